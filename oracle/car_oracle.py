@@ -1,0 +1,476 @@
+"""ORACLE — test infrastructure, NOT product code.
+
+CPU (or any torch device) restatement of the reference's per-ray rendering
+path ``CrossAttentionRenderer.forward(input, z=z)`` for n_view=2 with default
+flags (reference models.py:190-626).  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl
+reference`` leg may import this file; the product
+(``cross_attention_renderer_b200``) never does.
+
+Parity pinning: ``tests/test_oracle_golden.py`` checks this restatement
+against golden vectors produced by executing the unmodified reference in the
+build container (``tests/golden/make_golden.py``): integer outputs (bilinear
+tap indices, ``valid_mask``, ``at_wt_max``) exactly, floats to a few ulp at
+the geometry stages and 1e-5 relative downstream.
+
+Unlike the reference, every stage with a "bit-exact" claim (A.1-A.3: ray
+set-up, epipolar clipping, line samples) is written as scalar IEEE fp32
+operations in a fixed order with no fused multiply-add and no library
+matmul, so that a CUDA kernel using __fmul_rn/__fadd_rn/__fdiv_rn/__fsqrt_rn
+reproduces it bit for bit on any device.  Where the reference calls a
+matmul/bmm/norm whose internal order is a library detail (geometry.py:417,
+epipolar.py:25, F.normalize) the order chosen here is documented inline.
+
+Stage names A.0 ... A.12 follow SURVEY.md Appendix A.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+INF = float("inf")
+
+
+# ----------------------------------------------------------------------------
+# A.0  pose preparation (reference models.py:207-211, 285-286; geometry.py:404)
+# ----------------------------------------------------------------------------
+def prepare_cameras(inp):
+    """4x4 algebra the reference performs with torch.inverse/matmul.
+
+    Returns a dict of fp32 tensors:
+      Q     (b,n,4,4) inv(C) @ q            query cam2world in each ctx frame (models.py:208)
+      Cself (b,n,4,4) inv(C) @ C            ~identity, passed to get_3d_point_epipolar (:207,283)
+      Rel   (b,2,n,4,4) Rel[:,k] = inv(C[:,k]) @ C   ctx-j -> ctx-k (:285-286)
+      qinv  (b,4,4)   inv(query cam2world)  (geometry.py:404 via models.py:586)
+      K     (b,n,4,4) context intrinsics, Kq (b,4,4) query intrinsics
+    """
+    C = inp["context"]["cam2world"]
+    q = inp["query"]["cam2world"]
+    Cinv = torch.inverse(C)
+    out = {
+        "Q": torch.matmul(Cinv, q),
+        "Cself": torch.matmul(Cinv, C),
+        "Rel": torch.stack([torch.matmul(torch.inverse(C[:, k:k + 1]), C) for k in range(2)], dim=1),
+        "qinv": torch.inverse(q[:, 0]),
+        "K": inp["context"]["intrinsics"].clone(),
+        "Kq": inp["query"]["intrinsics"][:, 0].clone(),
+    }
+    return out
+
+
+# ----------------------------------------------------------------------------
+# helpers: fixed-order scalar arithmetic on tensors
+# ----------------------------------------------------------------------------
+def _dot3(a0, a1, a2, b0, b1, b2):
+    """(a0*b0 + a1*b1) + a2*b2, each op rounded separately."""
+    return (a0 * b0 + a1 * b1) + a2 * b2
+
+
+def _norm3(x, y, z):
+    return torch.sqrt((x * x + y * y) + z * z)
+
+
+def _cross(a, b):
+    """a x b, components as (mul, mul, sub) — torch.cross (geometry.py:243)."""
+    return (a[1] * b[2] - a[2] * b[1],
+            a[2] * b[0] - a[0] * b[2],
+            a[0] * b[1] - a[1] * b[0])
+
+
+def _ray_through_pixel(u, v, fx, fy, cx, cy, M):
+    """Unit direction (in the frame M maps into) of the ray through pixel
+    (u, v), and its Plücker moment.  reference geometry.py:236-245 ->
+    get_ray_directions :426-433 -> world_from_xy_depth :409-419 -> lift
+    :353-371.
+
+    M: tuple of 12 broadcastable tensors, rows 0..2 of the 4x4 cam2world.
+    The einsum at geometry.py:417 is a K=4 dot; order used here:
+    ((M0*x + M1*y) + M2*1) + M3*1.
+    """
+    xl = (u - cx) / fx            # * z with z == 1 is exact (geometry.py:365)
+    yl = (v - cy) / fy
+    p = []
+    for r in range(3):
+        m0, m1, m2, m3 = M[4 * r:4 * r + 4]
+        p.append(((m0 * xl + m1 * yl) + m2) + m3)
+    ox, oy, oz = M[3], M[7], M[11]
+    dx, dy, dz = p[0] - ox, p[1] - oy, p[2] - oz
+    nrm = torch.clamp_min(_norm3(dx, dy, dz), 1e-12)       # F.normalize eps (geometry.py:432)
+    d = (dx / nrm, dy / nrm, dz / nrm)
+    m = _cross((ox, oy, oz), d)
+    return d, m
+
+
+def _rows(M):
+    """(…,4,4) -> 12 tensors (rows 0..2), each with shape (…, 1) for ray broadcast."""
+    return tuple(M[..., r, c].unsqueeze(-1) for r in range(3) for c in range(4))
+
+
+# ----------------------------------------------------------------------------
+# A.1  query ray in each context frame  (models.py:213-217)
+# ----------------------------------------------------------------------------
+def ray_setup(cams, uv):
+    """uv (b,R,2) pixel (x,y).  Returns d, m (each tuple of 3 (b,n,R)) and o (b,n,3)."""
+    Q = cams["Q"]                                           # (b,n,4,4)
+    Kq = cams["Kq"]                                         # (b,4,4)
+    fx = Kq[:, 0, 0][:, None, None]
+    fy = Kq[:, 1, 1][:, None, None]
+    cx = Kq[:, 0, 2][:, None, None]
+    cy = Kq[:, 1, 2][:, None, None]
+    u = uv[..., 0][:, None, :]                              # (b,1,R)
+    v = uv[..., 1][:, None, :]
+    d, m = _ray_through_pixel(u, v, fx, fy, cx, cy, _rows(Q))
+    return d, m, Q[..., :3, 3]
+
+
+# ----------------------------------------------------------------------------
+# A.2  epipolar segment  (models.py:226-258 -> epipolar.py:175-253)
+# ----------------------------------------------------------------------------
+_EPS_LO = -1e-6           # epipolar.py:30,40  (python scalars are cast to fp32 by torch)
+_EPS_HI = 1 + 1e-6
+
+
+def _in_bounds(x, y):
+    """epipolar.py:28-35 (NaN compares false)."""
+    return (x >= _EPS_LO) & (y >= _EPS_LO) & (x <= _EPS_HI) & (y <= _EPS_HI)
+
+
+def _project_norm(px, py, pz, Kn):
+    """epipolar.py:23-26: p/(p.z+1e-8) then the 3x3 einsum, order (k0*x + k1*y) + k2*z."""
+    den = pz + 1e-8
+    qx, qy, qz = px / den, py / den, pz / den
+    x = (Kn[0][0] * qx + Kn[0][1] * qy) + Kn[0][2] * qz
+    y = (Kn[1][0] * qx + Kn[1][1] * qy) + Kn[1][2] * qz
+    return x, y
+
+
+def epipolar_segment(cams, d, o, H):
+    """Clip the query ray to each context image.  Returns start, end (b,n,R,2)
+    in grid coords [-1,1] after the NaN/Inf scrub, and overlaps (b,n,R) bool."""
+    K = cams["K"]
+    # intrinsics_norm: rows 0 AND 1 divided by H (models.py:228)
+    Kn = [[(K[..., r, c] / H).unsqueeze(-1) for c in range(3)] for r in range(2)]
+    ox, oy, oz = (o[..., i].unsqueeze(-1) for i in range(3))            # (b,n,1)
+    dx, dy, dz = d
+    oxyz = (ox, oy, oz)
+    dxyz = (dx, dy, dz)
+    shape = dx.shape
+    ts, xs, ys, vs = [], [], [], []
+    for dim, val in ((0, 0.0), (0, 1.0), (1, 0.0), (1, 1.0)):           # epipolar.py:196-201
+        od = 1 - dim
+        fs, fo = Kn[dim][dim], Kn[od][od]
+        cs, co = Kn[dim][2], Kn[od][2]
+        os_, oo = oxyz[dim], oxyz[od]
+        ds_, do = dxyz[dim], dxyz[od]
+        c = (val - cs) / fs                                            # epipolar.py:99
+        t = (c * oz - os_) / (ds_ - c * dz)                            # :103-105
+        num = fo * (oo * (c * dz - ds_) + do * (os_ - c * oz))         # :109
+        den = dz * os_ - ds_ * oz                                      # :110
+        other = co + num / den                                         # :111
+        same = torch.full(shape, val, dtype=other.dtype, device=other.device)
+        x, y = (same, other) if dim == 0 else (other, same)
+        zz = oz + t * dz                                               # :116 (z component)
+        valid = _in_bounds(x, y) & (zz > _EPS_LO)                      # :121
+        ts.append(t.expand(shape)); xs.append(x.expand(shape)); ys.append(y.expand(shape)); vs.append(valid.expand(shape))
+
+    def reduce(kind):                                                  # epipolar.py:125-149
+        lowest = INF if kind == "min" else -INF
+        bt = torch.where(vs[0], ts[0], torch.full_like(ts[0], lowest))
+        bx, by, bv = xs[0], ys[0], vs[0]
+        for i in range(1, 4):
+            ti = torch.where(vs[i], ts[i], torch.full_like(ts[i], lowest))
+            take = (ti < bt) if kind == "min" else (ti > bt)           # strict: first index wins ties
+            bt = torch.where(take, ti, bt)
+            bx = torch.where(take, xs[i], bx)
+            by = torch.where(take, ys[i], by)
+            bv = torch.where(take, vs[i], bv)
+        return bx, by, bv
+    fminx, fminy, fminv = reduce("min")
+    fmaxx, fmaxy, fmaxv = reduce("max")
+
+    # projection at t = 0 (epipolar.py:212-221)
+    depth_zero = (oz < 1e-6).expand(shape)
+    at_cam = (_norm3(ox, oy, oz) < 1e-6).expand(shape)
+    px = torch.where(at_cam, dx, ox.expand(shape))
+    py = torch.where(at_cam, dy, oy.expand(shape))
+    pz = torch.where(at_cam, dz, oz.expand(shape))
+    x0, y0 = _project_norm(px, py, pz, Kn)
+    v0 = _in_bounds(x0, y0) & (pz > _EPS_LO)
+    v0 = v0 & ~(depth_zero & ~at_cam)
+    # projection at t = inf (epipolar.py:226-230)
+    xi, yi = _project_norm(dx, dy, dz, Kn)
+    vi = _in_bounds(xi, yi) & (dz > _EPS_LO)
+    # merge (epipolar.py:241-251)
+    minx = torch.where(v0, x0, fminx); miny = torch.where(v0, y0, fminy); minv = v0 | fminv
+    maxx = torch.where(vi, xi, fmaxx); maxy = torch.where(vi, yi, fmaxy); maxv = vi | fmaxv
+    overlaps = minv & maxv
+
+    def to_grid(c):                                                    # models.py:246-252
+        g = (c - 0.5) * 2
+        return torch.where(torch.isfinite(g), g, torch.zeros_like(g))
+    start = torch.stack([to_grid(minx), to_grid(miny)], dim=-1)
+    end = torch.stack([to_grid(maxx), to_grid(maxy)], dim=-1)
+    return start, end, overlaps
+
+
+# ----------------------------------------------------------------------------
+# A.3  line samples (models.py:261, 271-275)
+# ----------------------------------------------------------------------------
+def line_samples(start, end, interval):
+    diff = end[..., None, :] - start[..., None, :]
+    return start[..., None, :] + diff * interval[None, None, None, :, None]   # (b,n,R,P,2)
+
+
+# ----------------------------------------------------------------------------
+# A.4 / A.6  bilinear gathers (PyTorch CUDA grid_sample formulas,
+#            ATen/native/cuda/GridSampler.cuh:23-31,56-59,139-168)
+# ----------------------------------------------------------------------------
+def bilinear_taps(gx, gy, w, h, border):
+    """Returns ix_nw, iy_nw (int64) and the 4 weights (nw, ne, sw, se)."""
+    ix = ((gx + 1.0) * w - 1.0) / 2.0
+    iy = ((gy + 1.0) * h - 1.0) / 2.0
+    if border:
+        ix = torch.clamp(torch.where(torch.isnan(ix), torch.zeros_like(ix), ix), 0, w - 1)
+        iy = torch.clamp(torch.where(torch.isnan(iy), torch.zeros_like(iy), iy), 0, h - 1)
+    bad = lambda c: (c > 2147483646.0) | (c < -2147483648.0) | ~torch.isfinite(c)
+    ix = torch.where(bad(ix), torch.full_like(ix, -100.0), ix)
+    iy = torch.where(bad(iy), torch.full_like(iy, -100.0), iy)
+    x0 = torch.floor(ix)
+    y0 = torch.floor(iy)
+    wx1 = ix - x0
+    wx0 = (x0 + 1) - ix
+    wy1 = iy - y0
+    wy0 = (y0 + 1) - iy
+    return x0.long(), y0.long(), (wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1)
+
+
+def gather_bilinear(maps, gx, gy, border):
+    """maps: list of (B,C,h,w); gx, gy (B,R,P).  Returns (B,R,P,sum C)."""
+    outs = []
+    B = gx.shape[0]
+    for zmap in maps:
+        _, C, h, w = zmap.shape
+        x0, y0, wts = bilinear_taps(gx, gy, w, h, border)
+        nhwc = zmap.permute(0, 2, 3, 1).reshape(B, h * w, C)
+        acc = torch.zeros(B, gx.shape[1], gx.shape[2], C, dtype=zmap.dtype, device=zmap.device)
+        for (ddx, ddy), wt in zip(((0, 0), (1, 0), (0, 1), (1, 1)), wts):
+            xx, yy = x0 + ddx, y0 + ddy
+            inb = (xx >= 0) & (xx < w) & (yy >= 0) & (yy < h)
+            idx = (yy.clamp(0, h - 1) * w + xx.clamp(0, w - 1)).reshape(B, -1)
+            vals = torch.gather(nhwc, 1, idx[..., None].expand(-1, -1, C)).reshape(*gx.shape, C)
+            acc = acc + vals * (wt * inb.to(wt.dtype))[..., None]
+        outs.append(acc)
+    return torch.cat(outs, dim=-1)
+
+
+# ----------------------------------------------------------------------------
+# A.5  triangulated point per sample, fp64 (geometry.py:98-162)
+# ----------------------------------------------------------------------------
+def triangulate(cams, d, m, pixel_val, H, W):
+    """pt (b,n,R,P,3) fp32: closest point on the query ray to the ray through
+    the context pixel, in that context's frame.  Also returns px, py."""
+    K = cams["K"]
+    fx = K[..., 0, 0][..., None, None]; fy = K[..., 1, 1][..., None, None]
+    cx = K[..., 0, 2][..., None, None]; cy = K[..., 1, 2][..., None, None]
+    px = (pixel_val[..., 0] + 1) / 2 * (W - 1)                        # geometry.py:101
+    py = (pixel_val[..., 1] + 1) / 2 * (H - 1)                        # :100
+    M = tuple(t.unsqueeze(-1) for t in _rows(cams["Cself"]))          # (b,n,1,1)
+    l2, m2 = _ray_through_pixel(px, py, fx, fy, cx, cy, M)            # :108
+    D = torch.float64
+    l1 = [t.unsqueeze(-1).to(D) for t in d]                           # (b,n,R,1)
+    m1 = [t.unsqueeze(-1).to(D) for t in m]
+    l2 = [t.to(D) for t in l2]
+    m2 = [t.to(D) for t in m2]
+    n = _cross(l1, l2)                                                # :142
+    a = _cross(l2, n)                                                 # :143
+    t1 = _cross(m1, a)                                                # :145 (negated below)
+    s = _dot3(m2[0], m2[1], m2[2], n[0], n[1], n[2])                  # :147
+    nn = _norm3(n[0], n[1], n[2])
+    cd = nn * nn + 1e-12                                              # :149
+    pt = []
+    for i in range(3):
+        p = (-t1[i] + s * l1[i]) / cd                                 # :151
+        p = torch.where(torch.isfinite(p), p, torch.zeros_like(p))    # :126-127
+        pt.append(p.to(torch.float32))
+    return torch.stack(pt, dim=-1), px, py
+
+
+# ----------------------------------------------------------------------------
+# A.6  cross-view reprojection (models.py:285-325; geometry.py:374-393; utils/util.py:16-19)
+# ----------------------------------------------------------------------------
+def _xform_point(T, pt):
+    """encode_relative_point (models.py:30-39): broadcast-multiply-sum with K=4,
+    order ((T0*x + T1*y) + T2*z) + T3."""
+    x, y, z = pt[..., 0], pt[..., 1], pt[..., 2]
+    out = []
+    for r in range(3):
+        t = [T[..., r, c][..., None, None] for c in range(4)]
+        out.append(((t[0] * x + t[1] * y) + t[2] * z) + t[3])
+    return torch.stack(out, dim=-1)
+
+
+def reproject(cams, pt, H, W):
+    """Returns pt_v0, pt_v1 (b,n,R,P,3): pt expressed in view-0 / view-1 frames
+    (raw, before the NaN scrub), and cross grid coords gxc, gyc (b,n,R,P):
+    for ctx-0 rows the projection into view 1, for ctx-1 rows into view 0."""
+    Rel = cams["Rel"]                                                 # (b,2,n,4,4)
+    K = cams["K"]
+    pt_v0 = _xform_point(Rel[:, 0], pt)
+    pt_v1 = _xform_point(Rel[:, 1], pt)
+    other = torch.stack([pt_v1[:, 0], pt_v0[:, 1]], dim=1)           # ctx0->view1, ctx1->view0
+    Ko = torch.stack([K[:, 1], K[:, 0]], dim=1)                      # intrinsics of the *other* view
+    fx = Ko[..., 0, 0][..., None, None]; fy = Ko[..., 1, 1][..., None, None]
+    cx = Ko[..., 0, 2][..., None, None]; cy = Ko[..., 1, 2][..., None, None]
+    X, Y, Z = other[..., 0], other[..., 1], other[..., 2]
+    xp = fx * X / (Z + 1e-12) + cx                                    # geometry.py:386
+    yp = fy * Y / (Z + 1e-12) + cy
+    big = torch.full_like(xp, 1e10)
+    xp = torch.where(torch.isfinite(xp), xp, big)                     # :390-391
+    yp = torch.where(torch.isfinite(yp), yp, big)
+    gxc = (xp / (W - 1)) * 2 - 1                                      # utils/util.py:17
+    gyc = (yp / (H - 1)) * 2 - 1
+    return pt_v0, pt_v1, gxc, gyc
+
+
+# ----------------------------------------------------------------------------
+# A.7 - A.12  per-sample MLPs, attention, colour MLP
+# ----------------------------------------------------------------------------
+def _lin(sd, name, x):
+    w = sd[name + ".weight"]
+    return F.linear(x, w.reshape(w.shape[0], -1), sd[name + ".bias"])
+
+
+def local_coords(cams, d, o, pt, px, py):
+    """16-channel geometric query feature (models.py:494-528; geometry.py:313-324)."""
+    K = cams["K"]
+    fx = K[..., 0, 0][..., None, None]; fy = K[..., 1, 1][..., None, None]
+    cx = K[..., 0, 2][..., None, None]; cy = K[..., 1, 2][..., None, None]
+    rx = (px - cx) / fx
+    ry = (py - cy) / fy
+    rz = torch.ones_like(rx)
+    nrm = torch.clamp_min(_norm3(rx, ry, rz), 1e-12)
+    cam = torch.stack([rx / nrm, ry / nrm, rz / nrm], dim=-1)
+    oo = o[:, :, None, None, :]
+    df = pt - oo
+    depth = _norm3(df[..., 0], df[..., 1], df[..., 2])
+    depth = torch.where(torch.isfinite(depth), depth, torch.full_like(depth, 1000000.0))
+    dd = torch.stack([t.unsqueeze(-1).expand_as(px) for t in d], dim=-1)
+    de = torch.stack([torch.tanh(depth), torch.tanh(depth / 10.), torch.tanh(depth / 100.),
+                      torch.tanh(depth / 1000.)], dim=-1)
+    return torch.cat([cam, torch.zeros_like(cam), dd, de, oo.expand_as(cam)], dim=-1)
+
+
+def _nan_to_num(x):
+    return torch.nan_to_num(x, 0)                                     # models.py:322-325
+
+
+def render(sd, inp, z, H, W, P, interval=None, cams=None):
+    """Full hot path.  sd: renderer state_dict (fp32), inp: reference-style input
+    dict, z: [z1,z2,z3] NCHW.  Returns dict with every out_dict entry of the
+    reference (models.py:217-218,570-571,592-597,617-624) and the intermediates."""
+    dev = z[0].device
+    b, n = inp["context"]["cam2world"].shape[:2]
+    assert n == 2
+    uv = inp["query"]["uv"][:, 0]                                     # (b,R,2)
+    R = uv.shape[1]
+    if cams is None:
+        cams = prepare_cameras(inp)
+    if interval is None:
+        interval = torch.linspace(0, 1, P, device=dev)                # models.py:261
+    I = {}
+    d, m, o = ray_setup(cams, uv)
+    start, end, overlaps = epipolar_segment(cams, d, o, H)
+    pv = line_samples(start, end, interval)                           # (b,n,R,P,2)
+    I["pixel_val"] = pv
+    gx, gy = pv[..., 0], pv[..., 1]
+    zmaps = [t.reshape(b, n, *t.shape[1:]) for t in z]
+    flat = lambda t: t.reshape(b * n, *t.shape[2:])
+    f_own = gather_bilinear(z, flat(gx), flat(gy), border=True).reshape(b, n, R, P, -1)
+    pt, px, py = triangulate(cams, d, m, pv, H, W)
+    pt_v0, pt_v1, gxc, gyc = reproject(cams, pt, H, W)
+    I["grid_cross"] = torch.stack([gxc, gyc], dim=-1)
+    # features of the OTHER view at the reprojected point (models.py:316-320)
+    z_other = [torch.stack([t[:, 1], t[:, 0]], dim=1).reshape(b * n, *t.shape[2:]) for t in zmaps]
+    f_oth = gather_bilinear(z_other, flat(gxc), flat(gyc), border=False).reshape(b, n, R, P, -1)
+    I["feat_primary"], I["feat_cross"] = f_own, f_oth
+    # per-row view-0 / view-1 features and points (models.py:330-342)
+    ctx0 = torch.zeros(1, n, 1, 1, 1, dtype=torch.bool, device=dev); ctx0[:, 0] = True
+    f_v0 = torch.where(ctx0, f_own, f_oth)
+    f_v1 = torch.where(ctx0, f_oth, f_own)
+    x_v0 = torch.cat([f_v0, torch.tanh(_nan_to_num(pt_v0) / 5.)], dim=-1)
+    x_v1 = torch.cat([f_v1, torch.tanh(_nan_to_num(pt_v1) / 5.)], dim=-1)
+    enc = lambda x: _lin(sd, "query_encode_latent_2", F.relu(_lin(sd, "query_encode_latent", x)))
+    e0, e1 = enc(x_v0), enc(x_v1)
+    interp = torch.cat([e0, e1], dim=-1)                              # (b,n,R,P,576)
+    I["enc_v0"], I["enc_v1"] = e0, e1
+    V = _lin(sd, "latent_value", interp)                              # models.py:487
+    Kk = _lin(sd, "key_map_2", F.relu(_lin(sd, "key_map", interp)))   # :491
+    loc = local_coords(cams, d, o, pt, px, py)                        # :494-528
+    Q1 = _lin(sd, "query_embed_2", F.relu(_lin(sd, "query_embed", loc)))   # :529
+    I.update(value=V, key=Kk, q1=Q1, local=loc, pt=pt)
+
+    def joint_softmax(s):                                             # models.py:533-535
+        sj = s.permute(0, 2, 1, 3).reshape(b, R, n * P)
+        a = F.softmax(sj, dim=-1)
+        return a.reshape(b, R, n, P).permute(0, 2, 1, 3)
+    s1 = (Kk * Q1).sum(-1) / 16.                                      # :532
+    a1 = joint_softmax(s1)                                            # (b,n,R,P)
+    zsum = (V * a1[..., None]).sum(dim=3).sum(dim=1)                  # (b,R,288)  :537-540
+    g = _lin(sd, "encode_latent", zsum)                               # :548 (b,R,128)
+    qin = torch.cat([g[:, None, :, None, :].expand(-1, n, -1, P, -1), loc], dim=-1)   # :552
+    Q2 = _lin(sd, "query_repeat_embed_2", F.relu(_lin(sd, "query_repeat_embed", qin)))
+    s2 = (Q2 * Q1).sum(-1) / 16.                                      # :555
+    a2 = joint_softmax(s2)
+    zloc2 = (V * a2[..., None]).sum(dim=3) + zsum[:, None]            # :561  (b,n,R,288)
+    zfin = zloc2.sum(dim=1)                                           # :564
+    I.update(s1=s1, at_wt=a1, zsum=zsum, g=g, q2=Q2, s2=s2, at_wt2=a2, z_final=zfin)
+    # depth (models.py:573-594)
+    at_max = a1.argmax(dim=-1)                                        # (b,n,R)
+    w3d = (a1[..., None] * torch.clamp(pt, -100, 100)).sum(dim=3).sum(dim=1)    # (b,R,3)
+    qi = cams["qinv"]
+    zc = ((qi[:, 2, 0, None] * w3d[..., 0] + qi[:, 2, 1, None] * w3d[..., 1])
+          + qi[:, 2, 2, None] * w3d[..., 2]) + qi[:, 2, 3, None]
+    depth_ray = torch.clamp(zc, 0, 10)
+    # colour MLP (models.py:597-616; resnet_block_fc.py:132-168)
+    dd = torch.stack(d, dim=-1); mm = torch.stack(m, dim=-1)          # (b,n,R,3)
+    coords9 = torch.cat([dd, mm, o[:, :, None, :].expand(-1, -1, R, -1)], dim=-1)   # (b,n,R,9)
+    c18 = coords9.permute(0, 2, 1, 3).reshape(b, R, n * 9)
+    z576 = torch.cat([zfin, zfin], dim=-1)
+    x = _lin(sd, "phi.lin_in", c18)
+    for i in range(3):
+        x = x + _lin(sd, f"phi.lin_z.{i}", z576)
+        net = _lin(sd, f"phi.blocks.{i}.fc_0", F.relu(x))
+        x = x + _lin(sd, f"phi.blocks.{i}.fc_1", F.relu(net))
+    rgb = _lin(sd, "phi.lin_out", F.relu(x))
+    valid = overlaps.any(dim=1).float()                               # (b,R)
+    rgb = rgb * valid[..., None] + 1 * (1 - valid[..., None])
+    out = {
+        "rgb": rgb.reshape(b, 1, R, 3),
+        "valid_mask": valid[..., None],
+        "depth_ray": depth_ray[..., None],
+        "at_wt": a1.reshape(b * n, R, P),
+        "at_wts": [a1.reshape(b * n, R, P)],
+        "at_wt_max": at_max.reshape(b * n, R, 1),
+        "pixel_val": pv.reshape(b * n, R, P, 2),
+        "coords": coords9.reshape(b * n, R, 9),
+        "uv": inp["query"]["uv"],
+        "z": z,
+        "_overlaps": overlaps,
+        "_start": start, "_end": end,
+        "_cams": cams,
+        "_I": I,
+    }
+    return out
+
+
+def primary_taps(pixel_val, w, h):
+    """Integer NW taps of the primary (border) gather for a map of size (h,w)."""
+    x0, y0, _ = bilinear_taps(pixel_val[..., 0], pixel_val[..., 1], w, h, border=True)
+    return x0, y0
+
+
+def psnr(a, b):
+    """eval metric of the reference (experiment_scripts/eval_realestate10k.py:74-75,181)."""
+    a = (a + 1) / 2
+    b = (b + 1) / 2
+    return -10.0 * math.log10(max(float(((a - b) ** 2).mean()), 1e-20))
