@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""Benchmark of the per-ray rendering hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference ...                      # CPU arm (oracle port of the reference)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...     # one rank per GPU
+
+A "step" = one pass of CrossAttentionRenderer.forward(input, z=z) over one batch of
+synthetic scenes: 256x256 target rays, 2 source views, 64 epipolar samples, 12 scenes per
+GPU (BASELINE config 2; at N>1 every rank renders its own 12 scenes = config 3's layout,
+weak scaling, tiles all-gathered at the end of the step).  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from cross_attention_renderer_b200 import synthetic  # noqa: E402
+
+METRIC = "rendered rays/sec at 256x256, 64 epipolar samples, 2 source views"
+FLOP_PER_SAMPLE_VIEW_ENC1 = 2 * 579 * 576
+TAP_BYTES_PER_RAY = {4: 2 * 64 * 2 * 576 * 4 * 4, 2: 2 * 64 * 2 * 576 * 4 * 2}   # n*P*2 gathers*576ch*4 taps*elt
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_rays_per_s(H, P, rays, warm_rays, seed=0):
+    """Reference arm: the oracle port of the reference's PyTorch path on the host cores."""
+    from oracle import car_oracle as orc
+    torch.set_num_threads(os.cpu_count())
+    z = synthetic.make_features(1, H, seed=seed)
+    sd = synthetic.make_state_dict(seed=seed)
+
+    def run(n, s):
+        inp = synthetic.make_inputs(1, H, H, seed=s, rays=n)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            out = orc.render(sd, inp, z, H, H, P)
+        float(out["rgb"].sum())
+        return time.perf_counter() - t0
+    if warm_rays:
+        run(warm_rays, seed + 100)
+    dt = run(rays, seed)
+    return rays / dt, dt
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    H, P = args.size, args.samples
+    rays = args.cpu_rays
+    for _ in range(args.warmup):
+        cpu_oracle_rays_per_s(H, P, max(64, rays // 8), 0)
+    t_tot, n_tot = 0.0, 0
+    for i in range(args.steps):
+        rps, dt = cpu_oracle_rays_per_s(H, P, rays, 0, seed=i)
+        t_tot += dt; n_tot += rays
+    value = n_tot / t_tot
+    cores = torch.get_num_threads()
+    sample = f"{rays} of the {H * H} target rays of one scene per step, {H}x{H} maps, {P} samples, 2 views"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{H}x{H} target, 2 views, {P} samples (BASELINE config 2), bounded sample on host cores",
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("CAR_PRECISION", "fp32_simt"),
+                    choices=["fp32_simt", "fp32", "bf16"])
+    ap.add_argument("--scenes", type=int, default=12, help="scenes per GPU")
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--samples", type=int, default=64)
+    ap.add_argument("--cpu-rays", type=int, default=2048)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch.distributed as dist
+    from cross_attention_renderer_b200 import _lib, sharding
+    from cross_attention_renderer_b200.models import CrossAttentionRenderer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    b, H, P = args.scenes, args.size, args.samples
+    R = H * H
+    lib = _lib.load()
+    # this rank's scenes (weak scaling: per-GPU work is fixed)
+    inp_h = synthetic.make_inputs(b, H, H, seed=100 + rank)
+    z_h = synthetic.make_features(b, H, seed=100 + rank)
+    sd = synthetic.make_state_dict(seed=0)
+    pin = lambda t: t.pin_memory()
+    inp_h = {k: {kk: pin(vv) for kk, vv in v.items()} for k, v in inp_h.items()}
+    z_h = [pin(t) for t in z_h]
+    model = CrossAttentionRenderer(n_view=2, npoints=P, precision=args.precision).to(dev)
+    model.load_state_dict(sd, strict=False)
+    model.H = model.W = H
+    model.pixel_val_to_cpu = False          # metric excludes the optional pixel_val D2H
+    inp_d = synthetic.to_device(inp_h, dev)
+    z_d = [t.to(dev) for t in z_h]
+    total_rays = b * R * world
+
+    def step_resident():
+        model._fcache = None                # re-pack NCHW->NHWC every step (no cached work)
+        with torch.no_grad():
+            out = model(inp_d, z=z_d)
+        if world > 1:                       # final gather of rendered tiles (north_star)
+            for k in ("rgb", "valid_mask", "depth_ray"):
+                t = out[k].reshape(b * R, -1)
+                recv = torch.empty(world * t.shape[0], t.shape[1], device=dev, dtype=t.dtype)
+                dist.all_gather_into_tensor(recv, t.contiguous())
+        return out
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    nst = len(_lib.STAGES)
+    import ctypes as C
+    ms_arr, ln_arr = (C.c_float * nst)(), (C.c_int * nst)()
+    lib.car_profile_begin()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step_resident()
+    ev1.record()
+    sync_all()
+    ms_total = ev0.elapsed_time(ev1)
+    lib.car_profile_end(ms_arr, ln_arr, nst)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    launches_per_step = model.last_launch_count + 3
+    value = total_rays * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers ------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h2d = sum(t_.numel() * t_.element_size() for t_ in z_h) + \
+            sum(v.numel() * v.element_size() for d_ in inp_h.values() for v in d_.values())
+        d2h = (b * R * 3 + b * R + b * R) * 4
+
+        def step_e2e():
+            inp_g = synthetic.to_device(inp_h, dev)      # H2D from pinned memory
+            z_g = [t_.to(dev, non_blocking=True) for t_ in z_h]
+            with torch.no_grad():
+                o = model(inp_g, z=z_g)
+            return o["rgb"].cpu(), o["valid_mask"].cpu(), o["depth_ray"].cpu()   # D2H of the result
+        step_e2e()
+        sync_all()
+        t0 = time.perf_counter()
+        n_e2e = max(2, min(args.steps, 3))
+        for _ in range(n_e2e):
+            step_e2e()
+        sync_all()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": total_rays * n_e2e / float(tt.item()), "unit": "rays/s",
+               "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "steps": n_e2e}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel + the gather -------------------------------------
+    peaks = measured_peaks()
+    stage_ms = {n: float(ms_arr[i]) for i, n in enumerate(_lib.STAGES)}
+    stage_ln = {n: int(ln_arr[i]) for i, n in enumerate(_lib.STAGES)}
+    dom = max(stage_ms, key=stage_ms.get)
+    rays_prof = b * R * args.steps                       # rank-0 rays covered by the profile
+    feat_elt = 2 if (args.precision == "bf16") else 4
+    tap_bytes = TAP_BYTES_PER_RAY[feat_elt] * (P / 64.0)
+    roof = {}
+    if stage_ms["gather"] > 0:
+        ach = rays_prof * tap_bytes / (stage_ms["gather"] * 1e-3) / 1e9
+        roof["gather"] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                          "frac": ach / peaks["hbm_gbs"], "traffic": None, "kernel": "k_gather",
+                          "avg_launch_ms": stage_ms["gather"] / max(1, stage_ln["gather"]),
+                          "algorithmic_bytes_per_ray": tap_bytes, "peak_source": peaks["source"]}
+    if stage_ms["gemm_enc1"] > 0:
+        fl = rays_prof * 2 * P * 2 * FLOP_PER_SAMPLE_VIEW_ENC1
+        ach = fl / (stage_ms["gemm_enc1"] * 1e-3) / 1e12
+        roof["gemm_enc1"] = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
+                             "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                             "kernel": "k_gemm_simt (fp32 FFMA)" if args.precision == "fp32_simt" else "k_gemm_umma",
+                             "avg_launch_ms": stage_ms["gemm_enc1"] / max(1, stage_ln["gemm_enc1"]),
+                             "peak_source": peaks["source"] + " bf16 dense, sustained"}
+    roofline = roof.get(dom) or roof.get("gemm_enc1") or roof.get("gather")
+    share = {k: round(v / max(1e-9, sum(stage_ms.values())), 4) for k, v in stage_ms.items() if v > 0}
+
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        rps, dt = cpu_oracle_rays_per_s(H, P, args.cpu_rays, 128)
+        cpu_base = {"value": rps, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+                    "sample": f"{args.cpu_rays} rays of one {H}x{H}/{P}-sample scene, {dt:.1f} s"}
+    line = {
+        "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32_simt": "f32", "fp32": "f32 (3xbf16 tcgen05 split, fp32 accumulate)", "bf16": "bf16"}[args.precision],
+        "data": "synthetic",
+        "config": {"workload": f"{H}x{H} target, 2 views, {P} samples, fp32 maps, {b} scenes per GPU (BASELINE config 2)",
+                   "scenes_per_gpu": b, "rays_per_step": total_rays, "precision": args.precision,
+                   "parallelism": f"ray/scene sharding x{world}, all_gather of tiles",
+                   "l2": "inputs (feature maps %.0f MB per GPU) exceed the 126 MB L2" % (sum(t_.numel() * 4 for t_ in z_h) / 1e6),
+                   "repacked_every_step": True},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+        "roofline": roofline, "roofline_all": roof, "stage_share": share, "stage_ms_per_step":
+            {k: round(v / args.steps, 3) for k, v in stage_ms.items() if v > 0},
+        "cpu_baseline": cpu_base,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,86 @@
+// Shared declarations of the B200 per-ray renderer kernels (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "car_b200.h"
+
+#define CAR_GEOM_STRIDE 32   // floats per sample row in the geometry record
+
+// Geometry record layout (one row per epipolar sample), see car_debug::geom
+enum {
+  G_GX = 0, G_GY = 1,        // primary grid coords (pixel_val)
+  G_GXC = 2, G_GYC = 3,      // cross-view grid coords
+  G_T0 = 4,                  // tanh(pt in view-0 frame / 5) [3]
+  G_T1 = 7,                  // tanh(pt in view-1 frame / 5) [3]
+  G_PTC = 10,                // clamp(pt, -100, 100) [3], then 3 floats of padding
+  G_LOCAL = 16,              // local_coords [16] (16-byte aligned: it is a GEMM A operand)
+};
+
+// Per (ray, ctx) record produced by the ray set-up kernel.
+struct RaySeg {
+  float sx, sy, ex, ey;      // segment start / end in grid coords (after scrub)
+};
+
+namespace car {
+
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+// Profiling hooks (car_profile_begin/end): call around a kernel launch.
+void prof_pre(int stage, cudaStream_t st);
+void prof_post(cudaStream_t st);
+void set_stage(int stage);          // stage id applied to the following launches
+int cur_stage();
+struct StageScope {                 // RAII: tag launches in a scope
+  int prev;
+  explicit StageScope(int s) : prev(cur_stage()) { set_stage(s); }
+  ~StageScope() { set_stage(prev); }
+};
+
+// ---- car_geometry.cu (compiled with -fmad=false) -------------------------
+void launch_ray_setup(const car_render_args &a, int g0, int g1, RaySeg *seg, uint8_t *overlap,
+                      cudaStream_t st);
+void launch_sample_geometry(const car_render_args &a, int g0, int g1, const RaySeg *seg,
+                            float *geom, cudaStream_t st);
+
+// ---- car_gather.cu -------------------------------------------------------
+void launch_pack_features(const float *nchw, void *nhwc, int bn, int C, int h, int w, int bf16,
+                          cudaStream_t st);
+// Builds encoder inputs X[row][view][592] from the packed maps.
+//   out_f32 != null: fp32 rows; else bf16 hi (+lo if out_lo != null)
+void launch_gather(const car_render_args &a, int g0, int g1, const float *geom, float *out_f32,
+                   uint16_t *out_hi, uint16_t *out_lo, cudaStream_t st);
+
+// ---- car_gemm_simt.cu ------------------------------------------------------
+struct GemmEpi {
+  const float *bias;        // [N] or null
+  const float *row_bias;    // [M / rows_per_group][N] or null (per-ray bias)
+  int rows_per_group;
+  int relu_in;              // apply relu to A on load
+  int relu_out;
+  int accumulate;           // C += result
+};
+void launch_gemm_simt(const float *A, int lda, const float *W, int ldw, float *C, int ldc, int M,
+                      int N, int K, const GemmEpi &epi, cudaStream_t st);
+
+// ---- car_attention.cu ------------------------------------------------------
+void launch_attention1(const car_render_args &a, int g0, int g1, const float *key, const float *q1,
+                       const float *value, const float *geom, float *zsum, float *rowbias,
+                       cudaStream_t st);
+void launch_attention2(const car_render_args &a, int g0, int g1, const float *q2, const float *q1,
+                       const float *value, const float *zsum, float *zfin, cudaStream_t st);
+void launch_phi_prep(const car_render_args &a, int g0, int g1, float *c18, cudaStream_t st);
+void launch_finalize(const car_render_args &a, int g0, int g1, const float *rgb3,
+                     const uint8_t *overlap, cudaStream_t st);
+
+// ---- car_gemm_umma.cu ------------------------------------------------------
+struct UmmaOut {
+  float *f32;               // [M][ldc] fp32 output or null
+  uint16_t *hi, *lo;        // [M][ldc] bf16 split output or null
+  int ldc;
+};
+int launch_gemm_umma(const uint16_t *a_hi, const uint16_t *a_lo, int lda, const uint16_t *w_hi,
+                     const uint16_t *w_lo, int ldw, int M, int N, int K, int split3,
+                     const GemmEpi &epi, const UmmaOut &out, cudaStream_t st);
+
+}  // namespace car

@@ -1,0 +1,257 @@
+"""Drop-in ``CrossAttentionRenderer`` whose per-ray path runs in the sm_100a
+CUDA library behind include/car_b200.h.
+
+Mirrors the reference module's public surface (reference models.py:42-626):
+constructor arguments and defaults (:43), parameter names / shapes
+(``state_dict`` ABI, :96-145), ``get_z(input, val=False)`` (:148-188) and
+``forward(input, z=None, val=False, debug=False) -> dict`` (:190-626) with the
+same ``out_dict`` keys and layouts.  The 4x4 pose algebra stays in torch
+(plumbing); everything from ray set-up to the final white fill is CUDA.
+
+Not a fallback: rendering raises unless the tensors live on a CUDA device and
+the library is built.
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib, packing
+from .params import HOT_PATH_PARAMS
+
+
+class _ResnetBlockFC(nn.Module):
+    """Parameter container with the reference's names (resnet_block_fc.py:10-51)."""
+
+    def __init__(self, size):
+        super().__init__()
+        self.fc_0 = nn.Linear(size, size)
+        self.fc_1 = nn.Linear(size, size)
+        nn.init.constant_(self.fc_0.bias, 0.0)
+        nn.init.kaiming_normal_(self.fc_0.weight, a=0, mode="fan_in")
+        nn.init.constant_(self.fc_1.bias, 0.0)
+        nn.init.zeros_(self.fc_1.weight)
+
+
+class _ResnetFC(nn.Module):
+    """Parameter container for ``phi`` (resnet_block_fc.py:65-130); evaluated in CUDA."""
+
+    def __init__(self, d_in, n_blocks, d_out, d_latent, d_hidden):
+        super().__init__()
+        self.lin_in = nn.Linear(d_in, d_hidden)
+        self.lin_out = nn.Linear(d_hidden, d_out)
+        self.blocks = nn.ModuleList([_ResnetBlockFC(d_hidden) for _ in range(n_blocks)])
+        self.lin_z = nn.ModuleList([nn.Linear(d_latent, d_hidden) for _ in range(n_blocks)])
+        for lin in [self.lin_in, self.lin_out, *self.lin_z]:
+            nn.init.constant_(lin.bias, 0.0)
+            nn.init.kaiming_normal_(lin.weight, a=0, mode="fan_in")
+
+
+class CrossAttentionRenderer(nn.Module):
+    def __init__(self, no_sample=False, no_latent_concat=False, no_multiview=False,
+                 no_high_freq=False, model="midas_vit", uv=None, repeat_attention=True, n_view=1,
+                 npoints=64, num_hidden_units_phi=128, encoder=None, precision=None):
+        super().__init__()
+        self.n_view = n_view
+        self.npoints = 64 if n_view in (1, 2) else 48          # models.py:48-51
+        if npoints:
+            self.npoints = npoints
+        self.repeat_attention = repeat_attention
+        self.no_sample = no_sample
+        self.no_latent_concat = no_latent_concat
+        self.no_multiview = no_multiview
+        self.no_high_freq = no_high_freq
+        self.model = model
+        self.num_hidden_units_phi = num_hidden_units_phi
+        if model != "midas_vit":
+            raise NotImplementedError("only model='midas_vit' (576-channel features) is on the hot path")
+        if n_view != 2 or no_sample or no_latent_concat or not repeat_attention:
+            raise NotImplementedError(
+                "the B200 path covers n_view=2 with default flags (SURVEY.md §8); "
+                "n_view=1/3, no_sample, no_latent_concat are 'next' rows")
+        if num_hidden_units_phi != 128:
+            raise NotImplementedError("num_hidden_units_phi must be 128")
+        # image encoder: outside the hot path; plug in any module with the reference's
+        # encoder.forward(rgb, cam2world_encode, n_view) -> [path_2, path_1] contract
+        self.encoder = encoder
+        hidden = 128
+        latent = 512 + 64
+        self.conv_map = nn.Conv2d(3, 64, kernel_size=7, stride=1, padding=3)
+        self.query_encode_latent = nn.Conv2d(latent + 3, latent, 1)
+        self.query_encode_latent_2 = nn.Conv2d(latent, latent // 2, 1)
+        self.latent_dim = latent // 2
+        self.update_val_merge = nn.Conv2d(self.latent_dim * 2 + 6, self.latent_dim, 1)
+        self.latent_value = nn.Conv2d(self.latent_dim * n_view, self.latent_dim, 1)
+        self.key_map = nn.Conv2d(self.latent_dim * n_view, hidden, 1)
+        self.key_map_2 = nn.Conv2d(hidden, hidden, 1)
+        self.query_embed = nn.Conv2d(16, hidden, 1)
+        self.query_embed_2 = nn.Conv2d(hidden, hidden, 1)
+        self.hidden_dim = hidden
+        self.latent_avg_query = nn.Conv2d(9 + 16, hidden, 1)
+        self.latent_avg_query_2 = nn.Conv2d(hidden, hidden, 1)
+        self.latent_avg_key = nn.Conv2d(self.latent_dim, hidden, 1)
+        self.latent_avg_key_2 = nn.Conv2d(hidden, hidden, 1)
+        self.query_repeat_embed = nn.Conv2d(16 + 128, hidden, 1)
+        self.query_repeat_embed_2 = nn.Conv2d(hidden, hidden, 1)
+        self.latent_avg_repeat_query = nn.Conv2d(9 + 16 + 128, hidden, 1)
+        self.latent_avg_repeat_query_2 = nn.Conv2d(hidden, hidden, 1)
+        self.encode_latent = nn.Conv1d(self.latent_dim, 128, 1)
+        self.phi = _ResnetFC(n_view * 9, n_blocks=3, d_out=3, d_latent=self.latent_dim * n_view,
+                             d_hidden=num_hidden_units_phi)
+        # B200 knobs (not part of the reference API)
+        self.precision = precision or os.environ.get("CAR_PRECISION", "fp32_simt")
+        self.feature_dtype = None            # None: fp32 for fp32*, bf16 for bf16
+        self.pixel_val_to_cpu = True         # reference returns pixel_val on the host (models.py:570)
+        self.chunk_rays = None
+        self._wcache = None
+        self._fcache = None
+        self._ws = None
+        self.last_launch_count = 0
+
+    # ------------------------------------------------------------------ encoder side
+    def get_z(self, input, val=False):
+        """Feature maps [path_2 (256ch,H/4), path_1 (256ch,H/2), conv_map (64ch,H)]
+        (reference models.py:148-188).  Needs an ``encoder`` module."""
+        rgb = input["context"]["rgb"]
+        cam2world = input["context"]["cam2world"]
+        rel_cam2world = torch.matmul(torch.inverse(cam2world[:, :1]), cam2world)
+        rgb = torch.flatten(rgb, 0, 1).permute(0, -1, 1, 2)
+        self.H, self.W = rgb.shape[-2], rgb.shape[-1]
+        rgb = (rgb + 1) / 2
+        mean = rgb.new_tensor([0.485, 0.456, 0.406])[None, :, None, None]
+        std = rgb.new_tensor([0.229, 0.224, 0.225])[None, :, None, None]
+        rgb = (rgb - mean) / std                               # utils/util.py:21-31
+        enc = rel_cam2world.reshape(-1, 16)
+        if self.no_multiview:
+            enc = torch.zeros_like(enc)
+        if self.encoder is None:
+            raise RuntimeError(
+                "get_z needs an image encoder (out of the hot path, SURVEY.md §8f): pass "
+                "encoder=<module> to the constructor or call forward(input, z=[z1,z2,z3])")
+        z = list(self.encoder.forward(rgb, enc, self.n_view))
+        z_conv = self.conv_map(rgb)
+        if self.no_high_freq:
+            z_conv = torch.zeros_like(z_conv)
+        return z + [z_conv]
+
+    # ------------------------------------------------------------------ caches
+    def _packed_weights(self):
+        params = dict(self.named_parameters())
+        key = tuple((params[n].data_ptr(), params[n]._version) for n in HOT_PATH_PARAMS)
+        if self._wcache is None or self._wcache[0] != key:
+            sd = {n: params[n].detach() for n in HOT_PATH_PARAMS}
+            self._wcache = (key, packing.PackedWeights(sd))
+        return self._wcache[1]
+
+    def _packed_features(self, z, bf16):
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in z) + (bf16,)
+        if self._fcache is None or self._fcache[0] != key:
+            self._fcache = (key, packing.pack_features([t.detach().float() for t in z], bf16))
+        return self._fcache[1]
+
+    def _workspace(self, nbytes, device):
+        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != device:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return self._ws
+
+    # ------------------------------------------------------------------ the hot path
+    def forward(self, input, z=None, val=False, debug=False, ray_range=None, debug_taps=None):
+        lib = _lib.load()
+        query, context = input["query"], input["context"]
+        b, n_context = context["rgb"].shape[:2]
+        n_qry, R = query["uv"].shape[1:3]
+        if n_context != 2 or n_qry != 1:
+            raise NotImplementedError("hot path: 2 context views, 1 query view")
+        if z is None:
+            z = z_orig = self.get_z(input)
+        else:
+            z_orig = z
+        dev = z[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("CrossAttentionRenderer (B200) has no CPU path: tensors must be on a CUDA device")
+        if not hasattr(self, "H"):
+            self.H, self.W = z[2].shape[-2], z[2].shape[-1]
+        H, W, P = self.H, self.W, self.npoints
+        if tuple(z[2].shape[-2:]) != (H, W) or z[0].shape[1] != 256 or z[2].shape[1] != 64:
+            raise ValueError("z must be [ (bn,256,H/4,W/4), (bn,256,H/2,W/2), (bn,64,H,W) ]")
+        prec = _lib.PRECISIONS[self.precision]
+        feat_bf16 = (self.feature_dtype == "bf16") if self.feature_dtype else (prec == _lib.PREC_BF16)
+
+        f32 = lambda t: t.to(device=dev, dtype=torch.float32)
+        Cm, q = f32(context["cam2world"]), f32(query["cam2world"])
+        Cinv = torch.inverse(Cm)                                        # models.py:207-208
+        cams = {
+            "Q": torch.matmul(Cinv, q).contiguous(),
+            "Cself": torch.matmul(Cinv, Cm).contiguous(),
+            "Rel": torch.stack([torch.matmul(torch.inverse(Cm[:, k:k + 1]), Cm) for k in range(2)],
+                               dim=1).contiguous(),                     # models.py:285-286
+            "qinv": torch.inverse(q[:, 0]).contiguous(),                # geometry.py:404
+            "K": f32(context["intrinsics"]).contiguous(),
+            "Kq": f32(query["intrinsics"])[:, 0].contiguous(),
+        }
+        uv = f32(query["uv"])[:, 0].contiguous()
+        interval = torch.linspace(0, 1, P, device=dev)                  # models.py:261
+        out = self.render_prepared(cams, uv, interval, z, b, R, ray_range=ray_range,
+                                   debug_taps=debug_taps)
+        out["uv"] = query["uv"]
+        out["z"] = z_orig
+        return out
+
+    def render_prepared(self, cams, uv, interval, z, b, R, ray_range=None, debug_taps=None):
+        """CUDA part of forward with the pose algebra already done (used directly by the
+        bit-exactness tests so both sides see identical 4x4 matrices)."""
+        lib = _lib.load()
+        dev = z[0].device
+        H, W, P = self.H, self.W, self.npoints
+        prec = _lib.PRECISIONS[self.precision]
+        feat_bf16 = (self.feature_dtype == "bf16") if self.feature_dtype else (prec == _lib.PREC_BF16)
+        pw = self._packed_weights()
+        feats = self._packed_features(z, feat_bf16)
+        total = b * R
+        g0, g1 = (0, total) if ray_range is None else ray_range
+        chunk = self.chunk_rays or lib.car_default_chunk_rays(prec, P)
+        chunk = max(1, min(chunk, g1 - g0))
+        ws = self._workspace(lib.car_workspace_bytes(prec, P, chunk), dev)
+        out = {
+            "rgb": torch.zeros(b, 1, R, 3, device=dev),
+            "valid_mask": torch.zeros(b, R, 1, device=dev),
+            "depth_ray": torch.zeros(b, R, 1, device=dev),
+            "at_wt": torch.zeros(b * 2, R, P, device=dev),
+            "at_wt_max": torch.zeros(b * 2, R, 1, dtype=torch.int64, device=dev),
+            "pixel_val": torch.zeros(b * 2, R, P, 2, device=dev),
+            "coords": torch.zeros(b * 2, R, 9, device=dev),
+        }
+        a = _lib.car_render_args()
+        a.abi_version = _lib.ABI_VERSION
+        a.precision = prec
+        a.b, a.R, a.P, a.H, a.W = b, R, P, H, W
+        a.ray_begin, a.ray_end = g0, g1
+        a.feat_bf16 = int(feat_bf16)
+        for i in range(3):
+            a.feat[i] = feats[i].data_ptr()
+        a.weights = pw.c_struct()
+        for k in ("Q", "Cself", "Rel", "qinv", "K", "Kq"):
+            assert cams[k].is_contiguous() and cams[k].dtype == torch.float32 and cams[k].device == dev
+            setattr(a.cams, k, cams[k].data_ptr())
+        a.uv, a.interval = uv.data_ptr(), interval.data_ptr()
+        for k, t in out.items():
+            setattr(a, k, t.data_ptr())
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        if debug_taps is not None:
+            rows = (g1 - g0) * 2 * P
+            shapes = {"geom": (rows, _lib.GEOM_STRIDE), "x": (rows, 2, _lib.K_ENC), "interp": (rows, 576),
+                      "value": (rows, 288), "key": (rows, 128), "q1": (rows, 128), "q2": (rows, 128),
+                      "zfinal": (g1 - g0, 288)}
+            for k, shp in shapes.items():
+                if k == "x" and prec != _lib.PREC_FP32_SIMT:
+                    continue
+                debug_taps[k] = torch.zeros(*shp, device=dev)
+                setattr(a.debug, k, debug_taps[k].data_ptr())
+        a.stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _lib.check(lib.car_render_forward(a), "car_render_forward")
+        self.last_launch_count = lib.car_last_launch_count()
+        out["at_wts"] = [out["at_wt"]]
+        if self.pixel_val_to_cpu:
+            out["pixel_val"] = out["pixel_val"].cpu()                   # models.py:570
+        return out

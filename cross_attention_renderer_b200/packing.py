@@ -1,0 +1,100 @@
+"""Weight packing: reference ``state_dict`` tensors -> the K-major matrices of
+``car_weights`` (include/car_b200.h).
+
+Pure re-layout done once per weight update with torch ops on the device
+(plumbing): every matrix becomes ``[N][K]`` fp32 with K zero-padded, plus its
+bf16 ``hi`` and ``lo = bf16(w - hi)`` halves for the tensor-core precisions.
+
+Two algebraic re-groupings (exact in real arithmetic, ~1 ulp in fp32):
+  * ``query_repeat_embed`` (144 -> 128, reference models.py:136,552-553) is
+    split into its per-ray block (columns 0..127, applied to
+    ``encode_latent(z_local)``) and its per-sample block (columns 128..143,
+    applied to ``local_coords``);
+  * ``phi.lin_z[i]`` (576 -> 128) sees the same 288-vector twice
+    (models.py:604-606), so its two column halves are summed.
+"""
+import torch
+
+from . import _lib
+
+
+def _split_bf16(w):
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return hi.contiguous(), lo.contiguous()
+
+
+class PackedMat:
+    def __init__(self, w, bias, k_pad=None):
+        w = w.detach().float().reshape(w.shape[0], -1)
+        if k_pad is not None and k_pad != w.shape[1]:
+            w = torch.nn.functional.pad(w, (0, k_pad - w.shape[1]))
+        self.f32 = w.contiguous()
+        self.hi, self.lo = _split_bf16(self.f32)
+        self.bias = None if bias is None else bias.detach().float().contiguous()
+        self.N, self.K = self.f32.shape
+
+    def c_struct(self):
+        m = _lib.car_mat()
+        m.f32 = self.f32.data_ptr()
+        m.hi = self.hi.data_ptr()
+        m.lo = self.lo.data_ptr()
+        m.bias = self.bias.data_ptr() if self.bias is not None else None
+        m.N, m.K = self.N, self.K
+        return m
+
+
+class PackedWeights:
+    """Holds the packed device tensors alive and exposes the ctypes struct."""
+
+    def __init__(self, sd):
+        g = lambda n: sd[n]
+        P = PackedMat
+        self.m = {}
+        self.m["enc1"] = P(g("query_encode_latent.weight"), g("query_encode_latent.bias"), _lib.K_ENC)
+        self.m["enc2"] = P(g("query_encode_latent_2.weight"), g("query_encode_latent_2.bias"))
+        self.m["value"] = P(g("latent_value.weight"), g("latent_value.bias"))
+        self.m["key1"] = P(g("key_map.weight"), g("key_map.bias"))
+        self.m["key2"] = P(g("key_map_2.weight"), g("key_map_2.bias"))
+        self.m["qry1"] = P(g("query_embed.weight"), g("query_embed.bias"))
+        self.m["qry2"] = P(g("query_embed_2.weight"), g("query_embed_2.bias"))
+        rep = g("query_repeat_embed.weight").reshape(128, 144)
+        self.m["rep1_g"] = P(rep[:, :128], g("query_repeat_embed.bias"))
+        self.m["rep1_loc"] = P(rep[:, 128:], None)
+        self.m["rep2"] = P(g("query_repeat_embed_2.weight"), g("query_repeat_embed_2.bias"))
+        self.m["enc_lat"] = P(g("encode_latent.weight"), g("encode_latent.bias"))
+        self.m["phi_in"] = P(g("phi.lin_in.weight"), g("phi.lin_in.bias"), 32)
+        for i in range(3):
+            wz = g(f"phi.lin_z.{i}.weight")
+            self.m[f"phi_z{i}"] = P(wz[:, :288] + wz[:, 288:], g(f"phi.lin_z.{i}.bias"))
+            self.m[f"phi_fc0{i}"] = P(g(f"phi.blocks.{i}.fc_0.weight"), g(f"phi.blocks.{i}.fc_0.bias"))
+            self.m[f"phi_fc1{i}"] = P(g(f"phi.blocks.{i}.fc_1.weight"), g(f"phi.blocks.{i}.fc_1.bias"))
+        self.m["phi_out"] = P(g("phi.lin_out.weight"), g("phi.lin_out.bias"))
+
+    def c_struct(self):
+        w = _lib.car_weights()
+        for name in ("enc1", "enc2", "value", "key1", "key2", "qry1", "qry2", "rep1_loc",
+                     "rep1_g", "rep2", "enc_lat", "phi_in", "phi_out"):
+            setattr(w, name, self.m[name].c_struct())
+        for i in range(3):
+            w.phi_z[i] = self.m[f"phi_z{i}"].c_struct()
+            w.phi_fc0[i] = self.m[f"phi_fc0{i}"].c_struct()
+            w.phi_fc1[i] = self.m[f"phi_fc1{i}"].c_struct()
+        return w
+
+
+def pack_features(z, bf16=False):
+    """[z1,z2,z3] NCHW fp32 (device) -> list of packed NHWC buffers via
+    car_pack_features.  One-off per scene batch."""
+    lib = _lib.load()
+    out = []
+    stream = torch.cuda.current_stream().cuda_stream
+    for t in z:
+        assert t.is_cuda and t.dtype == torch.float32, "features must be fp32 CUDA tensors"
+        t = t.contiguous()
+        bn, Cc, h, w = t.shape
+        o = torch.empty(bn, h, w, Cc, dtype=torch.bfloat16 if bf16 else torch.float32, device=t.device)
+        _lib.check(lib.car_pack_features(t.data_ptr(), o.data_ptr(), bn, Cc, h, w, int(bf16), stream),
+                   "car_pack_features")
+        out.append(o)
+    return out

@@ -1,0 +1,170 @@
+/*
+ * car_b200.h — C ABI of the B200-native per-ray rendering path.
+ *
+ * This is the drop-in boundary for the hot path of
+ * CrossAttentionRenderer.forward(input, z=z) (reference models.py:190-626):
+ * the reference has no native code, so these entry points are what a binding
+ * for that path binds (ctypes stub shown in INTEGRATION.md; the in-repo host
+ * side is cross_attention_renderer_b200/models.py).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless noted;
+ *     nothing is allocated or freed inside the library;
+ *   - every call enqueues work on the given cudaStream_t (passed as void*)
+ *     and returns without synchronising; calls are re-entrant per stream;
+ *   - return value: 0 = ok, <0 = argument error, >0 = cudaError_t of a failed
+ *     launch; car_last_error() returns a thread-local message.
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     point fails.
+ */
+#ifndef CAR_B200_H
+#define CAR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAR_ABI_VERSION 3
+
+/* Arithmetic of the per-sample MLP GEMMs (everything else is fp32/fp64). */
+enum car_precision {
+  CAR_PREC_FP32_SIMT = 0,   /* fp32 FFMA, exact fp32 accumulate (reference arithmetic)        */
+  CAR_PREC_FP32_3XBF16 = 1, /* tcgen05 kind::f16, operands split hi+lo bf16, 3 MMAs / product */
+  CAR_PREC_BF16 = 2         /* tcgen05 kind::f16, single bf16 MMA, fp32 accumulate            */
+};
+
+enum { CAR_C_FEAT = 576, CAR_C_LAT = 288, CAR_C_HID = 128, CAR_C_LOCAL = 16,
+       CAR_K_ENC = 592 /* 576 features + 3 tanh(pt/5) + 13 zero pad (multiple of 16) */ };
+
+int car_version(void);
+const char *car_last_error(void);
+
+/* ------------------------------------------------------------------------
+ * Feature maps.  The encoder returns z = [z1 (bn,256,H/4,W/4), z2 (bn,256,
+ * H/2,W/2), z3 (bn,64,H,W)] NCHW fp32 (reference models.py:178-188).  The
+ * gather wants channel-contiguous texels: one packed buffer per level,
+ * layout [bn][h][w][C], fp32 or bf16.  Replaces the NCHW reads of
+ * F.grid_sample at models.py:278,317.
+ * ---------------------------------------------------------------------- */
+size_t car_features_bytes(int bn, int H, int W, int level /*0,1,2*/, int bf16);
+int car_pack_features(const float *nchw, void *nhwc, int bn, int C, int h, int w,
+                      int bf16, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Weights, pre-packed by the host (cross_attention_renderer_b200/packing.py):
+ * every matrix is [N][K] row-major ("K-major"), K zero-padded to the stated
+ * value.  *_lo pointers are only read for CAR_PREC_FP32_3XBF16; for
+ * CAR_PREC_FP32_SIMT the f32 pointers are read and hi/lo ignored.
+ * Names follow the reference's state_dict (models.py:102-145).
+ * ---------------------------------------------------------------------- */
+typedef struct car_mat {
+  const float *f32;        /* [N][K] fp32                                   */
+  const uint16_t *hi;      /* [N][K] bf16  (round-to-nearest of f32)         */
+  const uint16_t *lo;      /* [N][K] bf16  (round-to-nearest of f32 - hi)    */
+  const float *bias;       /* [N] fp32                                      */
+  int32_t N, K;
+} car_mat;
+
+typedef struct car_weights {
+  car_mat enc1;      /* query_encode_latent      N=576 K=592 (579 padded)            */
+  car_mat enc2;      /* query_encode_latent_2    N=288 K=576                         */
+  car_mat value;     /* latent_value             N=288 K=576                         */
+  car_mat key1;      /* key_map                  N=128 K=576                         */
+  car_mat key2;      /* key_map_2                N=128 K=128                         */
+  car_mat qry1;      /* query_embed              N=128 K=16                          */
+  car_mat qry2;      /* query_embed_2            N=128 K=128                         */
+  car_mat rep1_loc;  /* query_repeat_embed[:,128:144]  N=128 K=16 (bias unused)      */
+  car_mat rep1_g;    /* query_repeat_embed[:,0:128]    N=128 K=128 (+ its bias)      */
+  car_mat rep2;      /* query_repeat_embed_2     N=128 K=128                         */
+  car_mat enc_lat;   /* encode_latent (Conv1d)   N=128 K=288                         */
+  car_mat phi_in;    /* phi.lin_in               N=128 K=32  (18 padded)             */
+  car_mat phi_z[3];  /* phi.lin_z.i folded: W[:, :288] + W[:, 288:]   N=128 K=288    */
+  car_mat phi_fc0[3];/* phi.blocks.i.fc_0        N=128 K=128                         */
+  car_mat phi_fc1[3];/* phi.blocks.i.fc_1        N=128 K=128                         */
+  car_mat phi_out;   /* phi.lin_out              N=3   K=128                         */
+} car_weights;
+
+/* ------------------------------------------------------------------------
+ * Cameras after the 4x4 pose algebra the reference does with torch.inverse /
+ * matmul (models.py:207-211,285-286; geometry.py:404).  All row-major fp32.
+ * ---------------------------------------------------------------------- */
+typedef struct car_cameras {
+  const float *Q;      /* (b,2,4,4)   inv(ctx c2w) @ query c2w                       */
+  const float *Cself;  /* (b,2,4,4)   inv(ctx c2w) @ ctx c2w                         */
+  const float *Rel;    /* (b,2,2,4,4) Rel[b][k][j] = inv(ctx_k c2w) @ ctx_j c2w       */
+  const float *qinv;   /* (b,4,4)     inv(query c2w)                                 */
+  const float *K;      /* (b,2,4,4)   context intrinsics (pixels)                    */
+  const float *Kq;     /* (b,4,4)     query intrinsics (pixels)                      */
+} car_cameras;
+
+/* Optional per-stage dumps for parity tests (any pointer may be NULL).
+ * Row index = ((scene*R + ray)*2 + ctx)*P + sample, restricted to the call's
+ * ray range; "view" = which context image the features came from. */
+typedef struct car_debug {
+  float *geom;      /* (rows,32): gx,gy,gxc,gyc, tanh(pt_v0/5)[3], tanh(pt_v1/5)[3], clamp(pt)[3], pad[3], local[16] */
+  float *x;         /* (rows,2,592) encoder inputs per view (fp32 modes only)                                      */
+  float *interp;    /* (rows,576)   [enc(view0) | enc(view1)]                                                      */
+  float *value;     /* (rows,288)                                                                                 */
+  float *key;       /* (rows,128)                                                                                 */
+  float *q1;        /* (rows,128)                                                                                 */
+  float *q2;        /* (rows,128)                                                                                 */
+  float *zfinal;    /* (rays,288)                                                                                 */
+} car_debug;
+
+typedef struct car_render_args {
+  int32_t abi_version;            /* CAR_ABI_VERSION                                         */
+  int32_t precision;              /* enum car_precision                                      */
+  int32_t b, R, P, H, W;          /* scenes, rays/scene, samples/line, context image size    */
+  int32_t ray_begin, ray_end;     /* this call renders flattened rays [ray_begin, ray_end)
+                                     of the b*R (scene-major) rays: the multi-GPU shard     */
+  int32_t feat_bf16;              /* packed features are bf16 (else fp32)                    */
+  const void *feat[3];            /* packed NHWC levels, (b*2, h_l, w_l, C_l)                */
+  car_weights weights;
+  car_cameras cams;
+  const float *uv;                /* (b,R,2) target pixel (x,y)  (models.py:198)             */
+  const float *interval;          /* (P) torch.linspace(0,1,P)   (models.py:261)             */
+  /* outputs: full-size tensors, only the ray range is written (models.py:217,570-621) */
+  float *rgb;                     /* (b,1,R,3)                                               */
+  float *valid_mask;              /* (b,R,1)                                                 */
+  float *depth_ray;               /* (b,R,1)                                                 */
+  float *at_wt;                   /* (b*2,R,P)  round-1 attention weights                    */
+  int64_t *at_wt_max;             /* (b*2,R,1)                                               */
+  float *pixel_val;               /* (b*2,R,P,2)                                             */
+  float *coords;                  /* (b*2,R,9)                                               */
+  void *workspace;                /* >= car_workspace_bytes(...)                             */
+  size_t workspace_bytes;
+  car_debug debug;                /* all-NULL in production                                  */
+  void *stream;                   /* cudaStream_t                                            */
+} car_render_args;
+
+/* Rays are processed in chunks of `chunk_rays`; workspace scales with the chunk. */
+size_t car_workspace_bytes(int precision, int P, int chunk_rays);
+int car_default_chunk_rays(int precision, int P);
+int car_render_forward(const car_render_args *args);
+
+/* Number of kernels the last car_render_forward on this thread launched. */
+int car_last_launch_count(void);
+
+/* Per-stage device timing for bench.py: between begin and end every kernel launch of this
+ * thread is bracketed by CUDA events recorded on the launching stream (no host sync while
+ * recording).  car_profile_end synchronises, adds the event durations per stage into
+ * ms[0..n) / launches[0..n) (HOST pointers) and stops recording. */
+enum car_stage { CAR_ST_RAYSETUP = 0, CAR_ST_SAMPLE_GEOM, CAR_ST_GATHER, CAR_ST_GEMM_ENC1,
+                 CAR_ST_GEMM_ENC2, CAR_ST_GEMM_KV, CAR_ST_GEMM_SMALL, CAR_ST_ATTENTION,
+                 CAR_ST_PHI, CAR_ST_PACK, CAR_ST_FUSED, CAR_ST_COUNT };
+int car_profile_begin(void);
+int car_profile_end(float *ms, int *launches, int n);
+
+/* Stand-alone tcgen05 GEMM used by the tensor-core precisions, exported for
+ * tests: C[M][N] = A[M][K] · W[N][K]^T (+bias) with A given as bf16 hi (+lo). */
+int car_gemm_umma_test(const uint16_t *a_hi, const uint16_t *a_lo, const uint16_t *w_hi,
+                       const uint16_t *w_lo, const float *bias, float *c, int M, int N, int K,
+                       int split3, int relu, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAR_B200_H */

@@ -1,0 +1,90 @@
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol
+include/car_b200.h declares, the ctypes structs match the C layout, and argument errors are
+reported without touching a GPU."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from cross_attention_renderer_b200 import _lib
+
+REPO = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+HEADER = os.path.join(REPO, "include", "car_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(_lib.lib_path()):
+        import __graft_entry__
+        __graft_entry__.build()
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    src = open(HEADER).read()
+    declared = set(re.findall(r"\b(car_[a-z0-9_]+)\s*\(", src))
+    assert declared, "no declarations found"
+    assert declared == set(_lib.SYMBOLS), (declared ^ set(_lib.SYMBOLS))
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_version(lib):
+    assert lib.car_version() == _lib.ABI_VERSION
+    m = re.search(r"#define CAR_ABI_VERSION (\d+)", open(HEADER).read())
+    assert int(m.group(1)) == _lib.ABI_VERSION
+
+
+def test_struct_layout_matches_c(tmp_path):
+    """Compile a C probe against the header and compare sizeof/offsetof with ctypes."""
+    probe = tmp_path / "probe.c"
+    probe.write_text('''
+#include <stdio.h>
+#include <stddef.h>
+#include "car_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu\\n", sizeof(car_mat), sizeof(car_weights), sizeof(car_cameras),
+         sizeof(car_debug), sizeof(car_render_args));
+  printf("%zu %zu %zu %zu %zu %zu\\n", offsetof(car_render_args, feat), offsetof(car_render_args, weights),
+         offsetof(car_render_args, cams), offsetof(car_render_args, uv),
+         offsetof(car_render_args, workspace_bytes), offsetof(car_render_args, stream));
+  return 0;
+}''')
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-I", os.path.join(REPO, "include"), str(probe), "-o", str(exe)], check=True)
+    lines = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    sizes = list(map(int, lines[0].split()))
+    offs = list(map(int, lines[1].split()))
+    A = _lib.car_render_args
+    assert sizes == [C.sizeof(_lib.car_mat), C.sizeof(_lib.car_weights), C.sizeof(_lib.car_cameras),
+                     C.sizeof(_lib.car_debug), C.sizeof(A)]
+    assert offs == [A.feat.offset, A.weights.offset, A.cams.offset, A.uv.offset,
+                    A.workspace_bytes.offset, A.stream.offset]
+
+
+def test_sizes_and_argument_errors(lib):
+    assert lib.car_features_bytes(2, 64, 64, 0, 0) == 2 * 16 * 16 * 256 * 4
+    assert lib.car_features_bytes(2, 64, 64, 2, 1) == 2 * 64 * 64 * 64 * 2
+    c = lib.car_default_chunk_rays(0, 64)
+    assert c >= 1
+    assert lib.car_workspace_bytes(0, 64, c) > lib.car_workspace_bytes(0, 64, 1) > 0
+    a = _lib.car_render_args()
+    a.abi_version = 1
+    assert lib.car_render_forward(C.byref(a)) == -2
+    assert b"ABI" in lib.car_last_error()
+    a.abi_version = _lib.ABI_VERSION
+    assert lib.car_render_forward(C.byref(a)) == -3          # sizes are all zero
+    assert lib.car_render_forward(None) == -1
+
+
+def test_no_cpu_fallback():
+    import torch
+    from cross_attention_renderer_b200 import synthetic
+    from cross_attention_renderer_b200.models import CrossAttentionRenderer
+    m = CrossAttentionRenderer(n_view=2, npoints=8)
+    inp = synthetic.make_inputs(1, 32, 8)
+    z = synthetic.make_features(1, 32)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(inp, z=z)
