@@ -303,9 +303,42 @@ namespace {
 // Tensor-core per-sample stage: same dataflow as sample_stage_simt with every GEMM on
 // tcgen05 (car_gemm_umma.cu), operands kept as bf16 hi(+lo) between stages.
 int sample_stage_umma(const car_render_args &a, const Workspace &w, int g0, int g1, cudaStream_t st) {
-  (void)a; (void)w; (void)g0; (void)g1; (void)st;
-  set_error("tensor-core precisions are not wired up yet");
-  return -9;
+  const car_weights &W = a.weights;
+  const int split3 = a.precision == CAR_PREC_FP32_3XBF16;
+  const int nr = g1 - g0;
+  const int rows = nr * 2 * a.P;
+  int rc;
+  auto out_bf = [&](uint16_t *hi, uint16_t *lo, int ldc, float *f32 = nullptr) {
+    UmmaOut o; o.f32 = f32; o.hi = hi; o.lo = split3 ? lo : nullptr; o.ldc = ldc; return o; };
+  auto out_f = [&](float *f32, int ldc) { UmmaOut o; o.f32 = f32; o.hi = nullptr; o.lo = nullptr; o.ldc = ldc; return o; };
+  auto mm = [&](const uint16_t *ah, const uint16_t *al, int lda, const car_mat &m, int M, const GemmEpi &e,
+                const UmmaOut &o) {
+    return launch_gemm_umma(ah, al, lda, m.hi, m.lo, m.K, M, m.N, m.K, split3, e, o, st);
+  };
+  launch_gather(a, g0, g1, w.geom, nullptr, w.x_hi, w.x_lo, st);
+  launch_split_rows(w.geom + G_LOCAL, CAR_GEOM_STRIDE, w.loc_hi, split3 ? w.loc_lo : nullptr, rows, 16, st);
+  // A.7 encoder MLP on both views of every sample: M = rows*2
+  { StageScope sc(CAR_ST_GEMM_ENC1);
+    if ((rc = mm(w.x_hi, w.x_lo, CAR_K_ENC, W.enc1, rows * 2, epi(W.enc1.bias, 1), out_bf(w.h1_hi, w.h1_lo, CAR_C_FEAT)))) return rc; }
+  { StageScope sc(CAR_ST_GEMM_ENC2);
+    if ((rc = mm(w.h1_hi, w.h1_lo, CAR_C_FEAT, W.enc2, rows * 2, epi(W.enc2.bias, 0),
+                 out_bf(w.in_hi, w.in_lo, CAR_C_LAT, a.debug.interp ? w.interp : nullptr)))) return rc; }
+  // A.8 value / key / geometric query
+  { StageScope sc(CAR_ST_GEMM_KV);
+    if ((rc = mm(w.in_hi, w.in_lo, CAR_C_FEAT, W.value, rows, epi(W.value.bias, 0), out_f(w.value, CAR_C_LAT)))) return rc;
+    if ((rc = mm(w.in_hi, w.in_lo, CAR_C_FEAT, W.key1, rows, epi(W.key1.bias, 1), out_bf(w.hid_hi, w.hid_lo, 128)))) return rc; }
+  if ((rc = mm(w.hid_hi, w.hid_lo, 128, W.key2, rows, epi(W.key2.bias, 0), out_f(w.key, 128)))) return rc;
+  if ((rc = mm(w.loc_hi, w.loc_lo, 16, W.qry1, rows, epi(W.qry1.bias, 1), out_bf(w.hid_hi, w.hid_lo, 128)))) return rc;
+  if ((rc = mm(w.hid_hi, w.hid_lo, 128, W.qry2, rows, epi(W.qry2.bias, 0), out_f(w.q1, 128)))) return rc;
+  launch_attention1(a, g0, g1, w.key, w.q1, w.value, w.geom, w.zsum, nullptr, st);
+  // per-ray 288->128->128 (M = rays): exact fp32
+  gemm(w.zsum, CAR_C_LAT, W.enc_lat, w.g, 128, nr, epi(W.enc_lat.bias, 0), st);
+  gemm(w.g, 128, W.rep1_g, w.rowbias, 128, nr, epi(W.rep1_g.bias, 0), st);
+  if ((rc = mm(w.loc_hi, w.loc_lo, 16, W.rep1_loc, rows, epi(nullptr, 1, 0, 0, w.rowbias, 2 * a.P),
+               out_bf(w.hid_hi, w.hid_lo, 128)))) return rc;
+  if ((rc = mm(w.hid_hi, w.hid_lo, 128, W.rep2, rows, epi(W.rep2.bias, 0), out_f(w.q2, 128)))) return rc;
+  launch_attention2(a, g0, g1, w.q2, w.q1, w.value, w.zsum, w.zfin, st);
+  return 0;
 }
 }  // namespace
 }  // namespace car

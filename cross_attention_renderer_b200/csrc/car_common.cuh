@@ -51,6 +51,10 @@ void launch_pack_features(const float *nchw, void *nhwc, int bn, int C, int h, i
 void launch_gather(const car_render_args &a, int g0, int g1, const float *geom, float *out_f32,
                    uint16_t *out_hi, uint16_t *out_lo, cudaStream_t st);
 
+// fp32 rows (row stride src_stride) -> contiguous bf16 hi (+lo) rows of `width` columns
+void launch_split_rows(const float *src, int src_stride, uint16_t *hi, uint16_t *lo, int rows,
+                       int width, cudaStream_t st);
+
 // ---- car_gemm_simt.cu ------------------------------------------------------
 struct GemmEpi {
   const float *bias;        // [N] or null

@@ -191,7 +191,29 @@ k_gather(car_render_args a, int g0, int g1, const float *__restrict__ geom, OUT 
   }
 }
 
+__global__ void k_split_rows(const float *__restrict__ src, int src_stride, uint16_t *__restrict__ hi,
+                             uint16_t *__restrict__ lo, long n, int width) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long r = i / width;
+  int c = (int)(i - r * width);
+  uint16_t h, l;
+  split_bf16(src[r * src_stride + c], h, l);
+  hi[i] = h;
+  if (lo) lo[i] = l;
+}
+
 }  // namespace
+
+void launch_split_rows(const float *src, int src_stride, uint16_t *hi, uint16_t *lo, int rows,
+                       int width, cudaStream_t st) {
+  long n = (long)rows * width;
+  if (n <= 0) return;
+  prof_pre(CAR_ST_GEMM_SMALL, st);
+  k_split_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, src_stride, hi, lo, n, width);
+  prof_post(st);
+  count_launch();
+}
 
 void launch_pack_features(const float *nchw, void *nhwc, int bn, int C, int h, int w, int bf16,
                           cudaStream_t st) {
