@@ -14,11 +14,17 @@ tap indices, ``valid_mask``, ``at_wt_max``) exactly, floats to a few ulp at
 the geometry stages and 1e-5 relative downstream.
 
 Unlike the reference, every stage with a "bit-exact" claim (A.1-A.3: ray
-set-up, epipolar clipping, line samples) is written as scalar IEEE fp32
-operations in a fixed order with no fused multiply-add and no library
-matmul, so that a CUDA kernel using __fmul_rn/__fadd_rn/__fdiv_rn/__fsqrt_rn
-reproduces it bit for bit on any device.  Where the reference calls a
-matmul/bmm/norm whose internal order is a library detail (geometry.py:417,
+set-up, epipolar clipping, line samples, and the integer bilinear taps
+derived from them) is written as scalar IEEE-754 fp32 operations in a fixed
+order with no fused multiply-add and no library matmul, so that a CUDA kernel
+using separately rounded mul/add/div/sqrt reproduces it bit for bit.  Those
+stages run on the ``X32`` wrapper below, which evaluates every fp32 operation
+in float64 and rounds once to fp32 (exactly the IEEE result for + - * / sqrt):
+torch's own fp32 kernels are NOT a usable definition, because they differ
+between devices (measured on torch 2.11: CPU ``sqrt`` is not correctly rounded
+- 0.65 % of random inputs differ from ``sqrt.rn`` -, CUDA ``x / python_scalar``
+multiplies by the reciprocal; scripts/diag_ops.py).  Where the reference calls
+a matmul/bmm/norm whose internal order is a library detail (geometry.py:417,
 epipolar.py:25, F.normalize) the order chosen here is documented inline.
 
 Stage names A.0 ... A.12 follow SURVEY.md Appendix A.
@@ -29,6 +35,66 @@ import torch
 import torch.nn.functional as F
 
 INF = float("inf")
+
+
+class X32:
+    """fp32 tensor whose arithmetic is exactly-rounded IEEE binary32, evaluated through
+    float64 (double rounding is innocuous for + - * / sqrt since 53 >= 2*24 + 2).
+    Python scalars are first rounded to fp32, like literals with an ``f`` suffix."""
+    __slots__ = ("t",)
+
+    def __init__(self, t):
+        self.t = t.t if isinstance(t, X32) else t
+
+    @staticmethod
+    def _d(v):
+        if isinstance(v, X32):
+            return v.t.double()
+        if torch.is_tensor(v):
+            return v.double()
+        return float(torch.tensor(float(v), dtype=torch.float32))
+
+    @staticmethod
+    def _f(v):
+        if isinstance(v, X32):
+            return v.t
+        if torch.is_tensor(v):
+            return v
+        return float(torch.tensor(float(v), dtype=torch.float32))
+
+    def __add__(self, o): return X32((X32._d(self) + X32._d(o)).float())
+    def __radd__(self, o): return X32((X32._d(o) + X32._d(self)).float())
+    def __sub__(self, o): return X32((X32._d(self) - X32._d(o)).float())
+    def __rsub__(self, o): return X32((X32._d(o) - X32._d(self)).float())
+    def __mul__(self, o): return X32((X32._d(self) * X32._d(o)).float())
+    def __rmul__(self, o): return X32((X32._d(o) * X32._d(self)).float())
+    def __truediv__(self, o): return X32((X32._d(self) / X32._d(o)).float())
+    def __rtruediv__(self, o): return X32((X32._d(o) / X32._d(self)).float())
+    def __neg__(self): return X32(-self.t)
+    def __lt__(self, o): return self.t < X32._f(o)
+    def __le__(self, o): return self.t <= X32._f(o)
+    def __gt__(self, o): return self.t > X32._f(o)
+    def __ge__(self, o): return self.t >= X32._f(o)
+    def sqrt(self): return X32(torch.sqrt(self.t.double()).float())
+    def expand(self, shape): return X32(self.t.expand(shape))
+    def unsqueeze(self, d): return X32(self.t.unsqueeze(d))
+    @property
+    def shape(self): return self.t.shape
+
+
+def xwhere(c, a, b):
+    a, b = X32._f(a), X32._f(b)
+    if not torch.is_tensor(a):
+        a = torch.full_like(b, a)
+    if not torch.is_tensor(b):
+        b = torch.full_like(a, b)
+    return X32(torch.where(c, a, b))
+
+
+def xmax(a, s):
+    """fmaxf(a, s) for a scalar s (NaN in ``a`` yields ``s``, like CUDA fmaxf)."""
+    s = X32._f(s)
+    return X32(torch.where(a.t >= s, a.t, torch.full_like(a.t, s)))
 
 
 # ----------------------------------------------------------------------------
@@ -67,7 +133,8 @@ def _dot3(a0, a1, a2, b0, b1, b2):
 
 
 def _norm3(x, y, z):
-    return torch.sqrt((x * x + y * y) + z * z)
+    q = (x * x + y * y) + z * z
+    return q.sqrt() if isinstance(q, X32) else torch.sqrt(q)
 
 
 def _cross(a, b):
@@ -87,6 +154,8 @@ def _ray_through_pixel(u, v, fx, fy, cx, cy, M):
     The einsum at geometry.py:417 is a K=4 dot; order used here:
     ((M0*x + M1*y) + M2*1) + M3*1.
     """
+    u, v, fx, fy, cx, cy = (X32(t) for t in (u, v, fx, fy, cx, cy))
+    M = tuple(X32(t) for t in M)
     xl = (u - cx) / fx            # * z with z == 1 is exact (geometry.py:365)
     yl = (v - cy) / fy
     p = []
@@ -95,10 +164,10 @@ def _ray_through_pixel(u, v, fx, fy, cx, cy, M):
         p.append(((m0 * xl + m1 * yl) + m2) + m3)
     ox, oy, oz = M[3], M[7], M[11]
     dx, dy, dz = p[0] - ox, p[1] - oy, p[2] - oz
-    nrm = torch.clamp_min(_norm3(dx, dy, dz), 1e-12)       # F.normalize eps (geometry.py:432)
+    nrm = xmax(_norm3(dx, dy, dz), 1e-12)                  # F.normalize eps (geometry.py:432)
     d = (dx / nrm, dy / nrm, dz / nrm)
     m = _cross((ox, oy, oz), d)
-    return d, m
+    return tuple(t.t for t in d), tuple(t.t for t in m)
 
 
 def _rows(M):
@@ -149,9 +218,9 @@ def epipolar_segment(cams, d, o, H):
     in grid coords [-1,1] after the NaN/Inf scrub, and overlaps (b,n,R) bool."""
     K = cams["K"]
     # intrinsics_norm: rows 0 AND 1 divided by H (models.py:228)
-    Kn = [[(K[..., r, c] / H).unsqueeze(-1) for c in range(3)] for r in range(2)]
-    ox, oy, oz = (o[..., i].unsqueeze(-1) for i in range(3))            # (b,n,1)
-    dx, dy, dz = d
+    Kn = [[(X32(K[..., r, c]) / float(H)).unsqueeze(-1) for c in range(3)] for r in range(2)]
+    ox, oy, oz = (X32(o[..., i].unsqueeze(-1)) for i in range(3))       # (b,n,1)
+    dx, dy, dz = (X32(t) for t in d)
     oxyz = (ox, oy, oz)
     dxyz = (dx, dy, dz)
     shape = dx.shape
@@ -167,11 +236,11 @@ def epipolar_segment(cams, d, o, H):
         num = fo * (oo * (c * dz - ds_) + do * (os_ - c * oz))         # :109
         den = dz * os_ - ds_ * oz                                      # :110
         other = co + num / den                                         # :111
-        same = torch.full(shape, val, dtype=other.dtype, device=other.device)
+        same = X32(torch.full(shape, val, dtype=other.t.dtype, device=other.t.device))
         x, y = (same, other) if dim == 0 else (other, same)
         zz = oz + t * dz                                               # :116 (z component)
         valid = _in_bounds(x, y) & (zz > _EPS_LO)                      # :121
-        ts.append(t.expand(shape)); xs.append(x.expand(shape)); ys.append(y.expand(shape)); vs.append(valid.expand(shape))
+        ts.append(t.t.expand(shape)); xs.append(x.t.expand(shape)); ys.append(y.t.expand(shape)); vs.append(valid.expand(shape))
 
     def reduce(kind):                                                  # epipolar.py:125-149
         lowest = INF if kind == "min" else -INF
@@ -191,9 +260,9 @@ def epipolar_segment(cams, d, o, H):
     # projection at t = 0 (epipolar.py:212-221)
     depth_zero = (oz < 1e-6).expand(shape)
     at_cam = (_norm3(ox, oy, oz) < 1e-6).expand(shape)
-    px = torch.where(at_cam, dx, ox.expand(shape))
-    py = torch.where(at_cam, dy, oy.expand(shape))
-    pz = torch.where(at_cam, dz, oz.expand(shape))
+    px = xwhere(at_cam, dx, ox.expand(shape))
+    py = xwhere(at_cam, dy, oy.expand(shape))
+    pz = xwhere(at_cam, dz, oz.expand(shape))
     x0, y0 = _project_norm(px, py, pz, Kn)
     v0 = _in_bounds(x0, y0) & (pz > _EPS_LO)
     v0 = v0 & ~(depth_zero & ~at_cam)
@@ -201,12 +270,12 @@ def epipolar_segment(cams, d, o, H):
     xi, yi = _project_norm(dx, dy, dz, Kn)
     vi = _in_bounds(xi, yi) & (dz > _EPS_LO)
     # merge (epipolar.py:241-251)
-    minx = torch.where(v0, x0, fminx); miny = torch.where(v0, y0, fminy); minv = v0 | fminv
-    maxx = torch.where(vi, xi, fmaxx); maxy = torch.where(vi, yi, fmaxy); maxv = vi | fmaxv
+    minx = xwhere(v0, x0, fminx); miny = xwhere(v0, y0, fminy); minv = v0 | fminv
+    maxx = xwhere(vi, xi, fmaxx); maxy = xwhere(vi, yi, fmaxy); maxv = vi | fmaxv
     overlaps = minv & maxv
 
     def to_grid(c):                                                    # models.py:246-252
-        g = (c - 0.5) * 2
+        g = ((c - 0.5) * 2).t
         return torch.where(torch.isfinite(g), g, torch.zeros_like(g))
     start = torch.stack([to_grid(minx), to_grid(miny)], dim=-1)
     end = torch.stack([to_grid(maxx), to_grid(maxy)], dim=-1)
@@ -217,8 +286,8 @@ def epipolar_segment(cams, d, o, H):
 # A.3  line samples (models.py:261, 271-275)
 # ----------------------------------------------------------------------------
 def line_samples(start, end, interval):
-    diff = end[..., None, :] - start[..., None, :]
-    return start[..., None, :] + diff * interval[None, None, None, :, None]   # (b,n,R,P,2)
+    diff = X32(end[..., None, :]) - X32(start[..., None, :])
+    return (X32(start[..., None, :]) + diff * X32(interval[None, None, None, :, None])).t   # (b,n,R,P,2)
 
 
 # ----------------------------------------------------------------------------
@@ -227,8 +296,8 @@ def line_samples(start, end, interval):
 # ----------------------------------------------------------------------------
 def bilinear_taps(gx, gy, w, h, border):
     """Returns ix_nw, iy_nw (int64) and the 4 weights (nw, ne, sw, se)."""
-    ix = ((gx + 1.0) * w - 1.0) / 2.0
-    iy = ((gy + 1.0) * h - 1.0) / 2.0
+    ix = (((X32(gx) + 1.0) * float(w) - 1.0) / 2.0).t
+    iy = (((X32(gy) + 1.0) * float(h) - 1.0) / 2.0).t
     if border:
         ix = torch.clamp(torch.where(torch.isnan(ix), torch.zeros_like(ix), ix), 0, w - 1)
         iy = torch.clamp(torch.where(torch.isnan(iy), torch.zeros_like(iy), iy), 0, h - 1)
@@ -272,8 +341,8 @@ def triangulate(cams, d, m, pixel_val, H, W):
     K = cams["K"]
     fx = K[..., 0, 0][..., None, None]; fy = K[..., 1, 1][..., None, None]
     cx = K[..., 0, 2][..., None, None]; cy = K[..., 1, 2][..., None, None]
-    px = (pixel_val[..., 0] + 1) / 2 * (W - 1)                        # geometry.py:101
-    py = (pixel_val[..., 1] + 1) / 2 * (H - 1)                        # :100
+    px = ((X32(pixel_val[..., 0]) + 1.0) / 2.0 * float(W - 1)).t      # geometry.py:101
+    py = ((X32(pixel_val[..., 1]) + 1.0) / 2.0 * float(H - 1)).t      # :100
     M = tuple(t.unsqueeze(-1) for t in _rows(cams["Cself"]))          # (b,n,1,1)
     l2, m2 = _ray_through_pixel(px, py, fx, fy, cx, cy, M)            # :108
     D = torch.float64

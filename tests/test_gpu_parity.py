@@ -235,8 +235,10 @@ def test_full_size_properties(precision):
     assert torch.isfinite(rgb).all() and torch.isfinite(out["depth_ray"]).all()
     assert float(out["depth_ray"].min()) >= 0 and float(out["depth_ray"].max()) <= 10
     assert int(out["at_wt_max"].min()) >= 0 and int(out["at_wt_max"].max()) < P
-    pv = out["pixel_val"]
-    assert float(pv.abs().max()) <= 1.0 + 1e-4                            # samples stay on the image
+    # rays that overlap context j keep all their samples on that image
+    pv = out["pixel_val"].reshape(b, 2, R, P, 2)
+    on_image = (pv.abs() <= 1.0 + 1e-4).all(dim=-1).all(dim=-1)          # (b,2,R)
+    assert bool((on_image.any(dim=1) | ~vm).all())
     # determinism + permutation equivariance over rays
     out2 = run_cuda(model, inp, z)
     assert torch.equal(out2["rgb"], out["rgb"])
