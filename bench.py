@@ -157,7 +157,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("CAR_PRECISION", "fp32_simt"),
+    ap.add_argument("--precision", default=os.environ.get("CAR_PRECISION", "fp32"),
                     choices=["fp32_simt", "fp32", "bf16"])
     ap.add_argument("--scenes", type=int, default=12, help="scenes per GPU")
     ap.add_argument("--size", type=int, default=256)

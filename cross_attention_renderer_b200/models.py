@@ -99,7 +99,7 @@ class CrossAttentionRenderer(nn.Module):
         self.phi = _ResnetFC(n_view * 9, n_blocks=3, d_out=3, d_latent=self.latent_dim * n_view,
                              d_hidden=num_hidden_units_phi)
         # B200 knobs (not part of the reference API)
-        self.precision = precision or os.environ.get("CAR_PRECISION", "fp32_simt")
+        self.precision = precision or os.environ.get("CAR_PRECISION", "fp32")
         self.feature_dtype = None            # None: fp32 for fp32*, bf16 for bf16
         self.pixel_val_to_cpu = True         # reference returns pixel_val on the host (models.py:570)
         self.chunk_rays = None

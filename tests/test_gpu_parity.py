@@ -44,6 +44,17 @@ def cpu(t):
     return t.detach().cpu()
 
 
+def depth_close(got, ref_depth, got_w, ref_w, b):
+    """depth_ray = clamp((inv(q) . sum_i a_i * clamp(pt_i, +-100)).z, 0, 10) (models.py:577-590):
+    its error is bounded per ray by 100 * sqrt(3) * sum_i |delta a_i| (+ fp32 rounding of the
+    sum), so the tolerance follows the attention-weight error instead of being a constant."""
+    R, P = ref_w.shape[1], ref_w.shape[2]
+    dw = (got_w - ref_w).abs().reshape(b, 2, R, P).sum(dim=(1, 3))       # (b,R)
+    bound = 2e-4 + 175.0 * dw
+    err = (got - ref_depth)[..., 0].abs()
+    return bool((err <= bound).all()), float((err - bound).max())
+
+
 # ---------------------------------------------------------------------------------------
 # bit-exact epipolar samples (A.1-A.3) against the fixed-order oracle
 # ---------------------------------------------------------------------------------------
@@ -73,9 +84,11 @@ def test_epipolar_samples_bit_exact(mode, b, H, Ht, P):
                         o[:, :, None, :].expand(-1, -1, uv.shape[1], -1)], -1).reshape(b * 2, -1, 9)
     assert torch.equal(cpu(out["coords"]).view(torch.int32), coords.view(torch.int32))
     assert torch.equal(cpu(out["valid_mask"])[..., 0], overlaps.any(dim=1).float())
+    vm = cpu(out["valid_mask"])[..., 0].bool()
+    rgb = cpu(out["rgb"])[:, 0]
+    assert torch.equal(rgb[~vm], torch.ones_like(rgb[~vm]))          # white fill (models.py:615-616)
     if mode == "outside":
-        assert float(cpu(out["valid_mask"]).sum()) == 0
-        assert torch.equal(cpu(out["rgb"]), torch.ones_like(cpu(out["rgb"])))
+        assert int((~vm).sum()) > 0
 
 
 # ---------------------------------------------------------------------------------------
@@ -145,7 +158,8 @@ def test_outputs_vs_oracle(staged, precision):
     assert rel_err(rgb, ref["rgb"]) < RGB_REL_TOL[precision]
     assert abs(orc.psnr(rgb, ref["rgb"])) > 80
     assert torch.allclose(cpu(out["at_wt"]), ref["at_wt"], rtol=2e-3, atol=1e-6)
-    assert torch.allclose(cpu(out["depth_ray"]), ref["depth_ray"], rtol=1e-4, atol=1e-4)
+    ok, worst = depth_close(cpu(out["depth_ray"]), ref["depth_ray"], cpu(out["at_wt"]), ref["at_wt"], b)
+    assert ok, worst
     aw = ref["at_wt"]
     top2 = aw.topk(2, dim=-1).values
     decided = (top2[..., 0] - top2[..., 1]) > 1e-4 * top2[..., 0]
@@ -160,7 +174,10 @@ def test_outputs_vs_oracle(staged, precision):
 def test_golden_fixture(name):
     cfg, inp, z, sd, rec = load_case(name)
     model = make_model(sd, cfg["P"], cfg["H"])
-    out = run_cuda(model, inp, z)
+    # the fixture was produced with the reference's CPU pose algebra; use the same 4x4s (the GPU
+    # torch.inverse differs from the CPU one by ulps, which ill-conditioned rays amplify to ~1e-3;
+    # that wrapper path is covered by test_forward_wrapper_pose_algebra_on_gpu)
+    out = run_cuda(model, inp, z, cams=orc.prepare_cameras(inp), interval=torch.linspace(0, 1, cfg["P"]))
     assert rel_err(cpu(out["rgb"]), rec["out_rgb"]) < 1e-4
     assert torch.equal(cpu(out["valid_mask"]), rec["out_valid_mask"])
     assert (out["pixel_val"] - rec["out_pixel_val"]).abs().max() <= 1e-5
@@ -171,7 +188,8 @@ def test_golden_fixture(name):
         assert torch.equal(x0, gx0) and torch.equal(y0, gy0)
     assert torch.allclose(cpu(out["coords"]), rec["out_coords"], rtol=1e-5, atol=1e-6)
     assert torch.allclose(cpu(out["at_wt"]), rec["out_at_wt"], rtol=2e-3, atol=1e-6)
-    assert torch.allclose(cpu(out["depth_ray"]), rec["out_depth_ray"], rtol=1e-4, atol=1e-4)
+    ok, worst = depth_close(cpu(out["depth_ray"]), rec["out_depth_ray"], cpu(out["at_wt"]), rec["out_at_wt"], cfg["b"])
+    assert ok, worst
     aw = rec["out_at_wt"]
     top2 = aw.topk(2, dim=-1).values
     decided = (top2[..., 0] - top2[..., 1]) > 1e-4 * top2[..., 0]
@@ -247,11 +265,28 @@ def test_full_size_properties(precision):
     inp_p["query"]["uv"] = inp["query"]["uv"][:, :, perm]
     out3 = run_cuda(model, inp_p, z)
     assert torch.equal(out3["rgb"][:, :, :], out["rgb"][:, :, perm.to(DEV)])
-    # sub-sampled comparison with the oracle (128 random rays)
+    # sub-sampled comparison with the oracle (128 random rays), identical prepared cameras
     idx = perm[:128].sort().values
     inp_s = {"context": inp["context"], "query": dict(inp["query"])}
     inp_s["query"]["uv"] = inp["query"]["uv"][:, :, idx]
+    cams = orc.prepare_cameras(inp)
+    interval = torch.linspace(0, 1, P)
     with torch.no_grad():
-        ref = orc.render(sd, inp_s, z, H, H, P)
-    got = cpu(out["rgb"])[:, :, idx]
-    assert rel_err(got, ref["rgb"]) < 2e-4   # pose algebra runs on GPU here (torch.inverse differs in ulps)
+        ref = orc.render(sd, inp_s, z, H, H, P, interval=interval, cams=cams)
+    outc = run_cuda(model, inp, z, cams=cams, interval=interval)
+    got = cpu(outc["rgb"])[:, :, idx]
+    assert rel_err(got, ref["rgb"]) < 1e-4
+    assert torch.equal(cpu(outc["pixel_val"]).reshape(b, 2, R, P, 2)[:, :, idx].reshape(b * 2, -1, P, 2),
+                       ref["pixel_val"])
+
+
+def test_forward_wrapper_pose_algebra_on_gpu():
+    """forward() does the 4x4 pose algebra with torch on the GPU (as the reference would on a
+    GPU); its inverse differs from the CPU one by ulps, so compare by PSNR / loose bound."""
+    cfg, inp, z, sd, rec = load_case("c1_sparse")
+    model = make_model(sd, cfg["P"], cfg["H"])
+    out = run_cuda(model, inp, z)
+    assert orc.psnr(cpu(out["rgb"]), rec["out_rgb"]) > 60.0
+    assert rel_err(cpu(out["rgb"]), rec["out_rgb"]) < 5e-3
+    assert torch.equal(cpu(out["valid_mask"]), rec["out_valid_mask"])
+    assert out["pixel_val"].device.type == "cpu" and out["z"] is not None and "uv" in out
