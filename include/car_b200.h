@@ -164,6 +164,13 @@ int car_gemm_umma_test(const uint16_t *a_hi, const uint16_t *a_lo, const uint16_
                        const uint16_t *w_lo, const float *bias, float *c, int M, int N, int K,
                        int split3, int relu, void *stream);
 
+/* CTA-pair (cta_group::2) tcgen05 GEMM, the building block of the fused per-ray kernel, exported
+ * for tests: C[M][N] = A·W^T (+bias); N is processed as `nch` MMA chunks; `dump` (optional)
+ * receives the raw TMEM image [pairs*2][128 lanes][N/2] of each pair's first tile. */
+int car_gemm_pair_test(const uint16_t *a_hi, const uint16_t *a_lo, const uint16_t *w_hi,
+                       const uint16_t *w_lo, const float *bias, float *c, float *dump, int M, int N,
+                       int K, int nch, int split3, int relu, int max_pairs, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
