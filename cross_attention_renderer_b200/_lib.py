@@ -8,7 +8,7 @@ cross_attention_renderer_b200/csrc``).
 import ctypes as C
 import os
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 PREC_FP32_SIMT, PREC_FP32_3XBF16, PREC_BF16 = 0, 1, 2
 PRECISIONS = {"fp32_simt": PREC_FP32_SIMT, "fp32": PREC_FP32_3XBF16, "bf16": PREC_BF16}
 K_ENC = 592
@@ -32,7 +32,7 @@ class car_weights(C.Structure):
                 ("key2", car_mat), ("qry1", car_mat), ("qry2", car_mat), ("rep1_loc", car_mat),
                 ("rep1_g", car_mat), ("rep2", car_mat), ("enc_lat", car_mat), ("phi_in", car_mat),
                 ("phi_z", car_mat * 3), ("phi_fc0", car_mat * 3), ("phi_fc1", car_mat * 3),
-                ("phi_out", car_mat)]
+                ("phi_out", car_mat), ("kv_fold", car_mat)]
 
 
 class car_cameras(C.Structure):
@@ -55,7 +55,7 @@ class car_render_args(C.Structure):
                 ("rgb", c_fp), ("valid_mask", c_fp), ("depth_ray", c_fp), ("at_wt", c_fp),
                 ("at_wt_max", c_fp), ("pixel_val", c_fp), ("coords", c_fp),
                 ("workspace", c_fp), ("workspace_bytes", C.c_size_t),
-                ("debug", car_debug), ("stream", c_fp)]
+                ("debug", car_debug), ("stream", c_fp), ("use_fused", C.c_int32)]
 
 
 # every symbol include/car_b200.h declares: (restype, argtypes)
@@ -71,7 +71,7 @@ SYMBOLS = {
     "car_profile_begin": (C.c_int, []),
     "car_profile_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]),
     "car_gemm_umma_test": (C.c_int, [c_fp] * 6 + [C.c_int] * 5 + [c_fp]),
-    "car_gemm_pair_test": (C.c_int, [c_fp] * 7 + [C.c_int] * 7 + [c_fp]),
+    "car_gemm_pair_test": (C.c_int, [c_fp] * 7 + [C.c_int] * 8 + [c_fp]),
 }
 
 _lib = None

@@ -315,18 +315,24 @@ int sample_stage_umma(const car_render_args &a, const Workspace &w, int g0, int 
                 const UmmaOut &o) {
     return launch_gemm_umma(ah, al, lda, m.hi, m.lo, m.K, M, m.N, m.K, split3, e, o, st);
   };
-  launch_gather(a, g0, g1, w.geom, nullptr, w.x_hi, w.x_lo, st);
   launch_split_rows(w.geom + G_LOCAL, CAR_GEOM_STRIDE, w.loc_hi, split3 ? w.loc_lo : nullptr, rows, 16, st);
-  // A.7 encoder MLP on both views of every sample: M = rows*2
-  { StageScope sc(CAR_ST_GEMM_ENC1);
-    if ((rc = mm(w.x_hi, w.x_lo, CAR_K_ENC, W.enc1, rows * 2, epi(W.enc1.bias, 1), out_bf(w.h1_hi, w.h1_lo, CAR_C_FEAT)))) return rc; }
-  { StageScope sc(CAR_ST_GEMM_ENC2);
-    if ((rc = mm(w.h1_hi, w.h1_lo, CAR_C_FEAT, W.enc2, rows * 2, epi(W.enc2.bias, 0),
-                 out_bf(w.in_hi, w.in_lo, CAR_C_LAT, a.debug.interp ? w.interp : nullptr)))) return rc; }
-  // A.8 value / key / geometric query
-  { StageScope sc(CAR_ST_GEMM_KV);
-    if ((rc = mm(w.in_hi, w.in_lo, CAR_C_FEAT, W.value, rows, epi(W.value.bias, 0), out_f(w.value, CAR_C_LAT)))) return rc;
-    if ((rc = mm(w.in_hi, w.in_lo, CAR_C_FEAT, W.key1, rows, epi(W.key1.bias, 1), out_bf(w.hid_hi, w.hid_lo, 128)))) return rc; }
+  const bool fused = a.use_fused && a.P == 64 && W.kv_fold.hi && !a.debug.interp;
+  if (fused) {
+    // gather + enc1 + (enc2 ∘ [value; key1]) in one CTA-pair kernel: V and relu(key1) per sample
+    if ((rc = launch_fused_encode(a, g0, g1, w.geom, w.value, w.hid_hi, split3 ? w.hid_lo : nullptr, st))) return rc;
+  } else {
+    launch_gather(a, g0, g1, w.geom, nullptr, w.x_hi, w.x_lo, st);
+    // A.7 encoder MLP on both views of every sample: M = rows*2
+    { StageScope sc(CAR_ST_GEMM_ENC1);
+      if ((rc = mm(w.x_hi, w.x_lo, CAR_K_ENC, W.enc1, rows * 2, epi(W.enc1.bias, 1), out_bf(w.h1_hi, w.h1_lo, CAR_C_FEAT)))) return rc; }
+    { StageScope sc(CAR_ST_GEMM_ENC2);
+      if ((rc = mm(w.h1_hi, w.h1_lo, CAR_C_FEAT, W.enc2, rows * 2, epi(W.enc2.bias, 0),
+                   out_bf(w.in_hi, w.in_lo, CAR_C_LAT, a.debug.interp ? w.interp : nullptr)))) return rc; }
+    // A.8 value / key / geometric query
+    { StageScope sc(CAR_ST_GEMM_KV);
+      if ((rc = mm(w.in_hi, w.in_lo, CAR_C_FEAT, W.value, rows, epi(W.value.bias, 0), out_f(w.value, CAR_C_LAT)))) return rc;
+      if ((rc = mm(w.in_hi, w.in_lo, CAR_C_FEAT, W.key1, rows, epi(W.key1.bias, 1), out_bf(w.hid_hi, w.hid_lo, 128)))) return rc; }
+  }
   if ((rc = mm(w.hid_hi, w.hid_lo, 128, W.key2, rows, epi(W.key2.bias, 0), out_f(w.key, 128)))) return rc;
   if ((rc = mm(w.loc_hi, w.loc_lo, 16, W.qry1, rows, epi(W.qry1.bias, 1), out_bf(w.hid_hi, w.hid_lo, 128)))) return rc;
   if ((rc = mm(w.hid_hi, w.hid_lo, 128, W.qry2, rows, epi(W.qry2.bias, 0), out_f(w.q1, 128)))) return rc;

@@ -87,4 +87,8 @@ int launch_gemm_umma(const uint16_t *a_hi, const uint16_t *a_lo, int lda, const 
                      const uint16_t *w_lo, int ldw, int M, int N, int K, int split3,
                      const GemmEpi &epi, const UmmaOut &out, cudaStream_t st);
 
+// ---- car_fused.cu -----------------------------------------------------------------------
+int launch_fused_encode(const car_render_args &a, int g0, int g1, const float *geom, float *value,
+                        uint16_t *kh_hi, uint16_t *kh_lo, cudaStream_t st);
+
 }  // namespace car

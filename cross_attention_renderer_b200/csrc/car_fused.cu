@@ -1,0 +1,492 @@
+// Fused epipolar gather + per-sample encoder for one ray per CTA pair (P == 64).
+//
+// Replaces, for the tensor-core precisions, the chain
+//   k_gather -> GEMM query_encode_latent (+ReLU) -> GEMM query_encode_latent_2
+//            -> GEMM latent_value / GEMM key_map (+ReLU)
+// (reference models.py:278,317,333-344,487-491) by ONE kernel in which the 576/579-wide
+// per-sample activations never leave the SM:
+//
+//   CTA pair (cluster of 2, tcgen05 cta_group::2, UMMA M = 128): CTA `rank` owns the 64 samples of
+//   the ray's epipolar line in context view `rank`.
+//   for view v in {0,1}:                         (features of view v at every sample, A.7)
+//     GEMM1   acc1[128 x 576] = X_v[128 x 592] · W1^T        X_v produced IN the kernel:
+//             gather warps bilinearly sample the NHWC maps (own line: border taps, other view:
+//             re-projected zero-padded taps), convert to bf16 hi(+lo) and write 32-channel
+//             K-slices straight into the swizzled smem ring that feeds the MMA
+//     epilogue acc1 -> +bias, ReLU -> bf16 hi(+lo) -> smem ring (A operand of the next GEMM)
+//     GEMM3   acc3[128 x 416] += H1_v[128 x 576] · F_v^T     F = [latent_value; key_map]∘enc2 folded
+//   epilogue acc3 -> V (fp32, 288) and relu(key_map) (bf16 hi/lo, 128) per sample -> HBM
+//
+// TMEM (per CTA, 64 rows in the "2x2" layout => N/2 columns): acc1 288 + acc3 208 = 496 <= 512.
+// SMEM: X ring + H ring (A operands), B ring (W1 / F slices via TMA, each CTA loads its half of
+// every N chunk), tap table.  All operand tiles are K-major, 64-byte swizzle, 32 K per stage.
+#include <math.h>
+
+#include "car_common.cuh"
+#include "car_umma.cuh"
+
+namespace car {
+int make_tmap_bf16(CUtensorMap *tm, const uint16_t *base, int rows, int K, int ld, int box_rows, int box_k);
+
+namespace {
+using namespace ptx;
+
+constexpr int KS = 32;                 // K per stage (bf16 elements) = one 64-byte swizzle row
+constexpr int ROWS = 64;               // sample rows per CTA
+constexpr int NX = 4, NH = 4;          // X / H ring depth
+constexpr int N1 = 576, N1CH = 192, N1C = 3;      // GEMM1: 3 MMA chunks of 192
+constexpr int N3 = 416, N3CH = 208, N3C = 2;      // GEMM3: 2 MMA chunks of 208
+constexpr int K1_STAGES = 19;          // ceil(592 / 32); the last stage holds 16 valid columns
+constexpr int K3_STAGES = 18;          // 576 / 32
+constexpr int ACC1_COL = 0, ACC3_COL = 288;
+constexpr int PRODUCER_WARPS = 8;
+constexpr int THREADS = (2 + 4 + PRODUCER_WARPS) * 32;   // 448
+constexpr int MAXB = 6;
+
+struct TapEntry { int off[4]; float w[4]; };              // 32 bytes
+
+struct FusedParams {
+  const void *feat[3];
+  int H, W, R, g0, g1;
+  const float *geom;                   // (rows,32) for rays [g0,g1)
+  const float *bias1;                  // [576]
+  const float *biasf;                  // [416]
+  float *value;                        // (rows,288) fp32
+  uint16_t *kh_hi, *kh_lo;             // (rows,128) bf16: relu(key_map)
+  int nb;                              // B ring depth
+};
+
+template <int SPLIT> struct Cfg {
+  static constexpr int OPS = SPLIT == 3 ? 2 : 1;                  // hi (+lo) copies
+  static constexpr int A_HALF = ROWS * KS * 2;                     // 4096 B (hi part of an A stage)
+  static constexpr int A_STAGE = A_HALF * OPS;
+  static constexpr int W1_CHUNK = (N1CH / 2) * KS * 2;             // 6144 B
+  static constexpr int F_CHUNK = (N3CH / 2) * KS * 2;              // 6656 B
+  static constexpr int B_HALF = N1C * W1_CHUNK;                    // 18432 B (>= N3C*F_CHUNK = 13312)
+  static constexpr int B_STAGE = B_HALF * OPS;
+};
+
+__device__ __forceinline__ float downgrade(float x) {
+  if (x > 2147483646.0f || x < -2147483648.0f || !isfinite(x)) return -100.0f;
+  return x;
+}
+// Same arithmetic as car_gather.cu::make_taps (PyTorch CUDA grid_sample formulas).
+__device__ __forceinline__ TapEntry make_taps(float gx, float gy, int w, int h, bool border) {
+  float ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)w), 1.f), 2.f);
+  float iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)h), 1.f), 2.f);
+  if (border) {
+    ix = fminf((float)(w - 1), fmaxf(ix, 0.f));
+    iy = fminf((float)(h - 1), fmaxf(iy, 0.f));
+  }
+  ix = downgrade(ix);
+  iy = downgrade(iy);
+  float fx0 = floorf(ix), fy0 = floorf(iy);
+  int x0 = (int)fx0, y0 = (int)fy0;
+  float wx1 = __fsub_rn(ix, fx0), wx0 = __fsub_rn(__fadd_rn(fx0, 1.f), ix);
+  float wy1 = __fsub_rn(iy, fy0), wy0 = __fsub_rn(__fadd_rn(fy0, 1.f), iy);
+  TapEntry t;
+  t.w[0] = wx0 * wy0; t.w[1] = wx1 * wy0; t.w[2] = wx0 * wy1; t.w[3] = wx1 * wy1;
+  bool xin0 = x0 >= 0 && x0 < w, xin1 = x0 + 1 >= 0 && x0 + 1 < w;
+  bool yin0 = y0 >= 0 && y0 < h, yin1 = y0 + 1 >= 0 && y0 + 1 < h;
+  t.off[0] = (xin0 && yin0) ? y0 * w + x0 : -1;
+  t.off[1] = (xin1 && yin0) ? y0 * w + x0 + 1 : -1;
+  t.off[2] = (xin0 && yin1) ? (y0 + 1) * w + x0 : -1;
+  t.off[3] = (xin1 && yin1) ? (y0 + 1) * w + x0 + 1 : -1;
+  return t;
+}
+
+__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
+  float ra, rb, d0, d1;
+  hi = pack_bf16x2(a, b, ra, rb);
+  lo = pack_bf16x2(ra, rb, d0, d1);
+}
+
+template <int SPLIT, typename FT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_constant__ CUtensorMap tm_w1_lo,
+               const __grid_constant__ CUtensorMap tm_f_hi, const __grid_constant__ CUtensorMap tm_f_lo,
+               FusedParams p) {
+  using C = Cfg<SPLIT>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *xs = smem;                                       // NX x A_STAGE
+  uint8_t *hs = xs + NX * C::A_STAGE;                       // NH x A_STAGE
+  uint8_t *bs = hs + NH * C::A_STAGE;                       // nb x B_STAGE
+  TapEntry *taps = reinterpret_cast<TapEntry *>(bs + (size_t)p.nb * C::B_STAGE);   // [64][3][2]
+  float *tanhs = reinterpret_cast<float *>(taps + ROWS * 3 * 2);                   // [64][8]
+  float *sbias1 = tanhs + ROWS * 8;                                                // [576]
+  float *sbiasf = sbias1 + N1;                                                     // [416]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sbiasf + N3);
+  uint64_t *x_full = bars, *x_empty = x_full + NX;
+  uint64_t *h_full = x_empty + NX, *h_empty = h_full + NH;
+  uint64_t *b_full = h_empty + NH, *b_empty = b_full + MAXB;
+  uint64_t *a1_full = b_empty + MAXB, *a1_empty = a1_full + 1;
+  uint64_t *a3_full = a1_empty + 1, *a3_empty = a3_full + 1;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a3_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int nrays = p.g1 - p.g0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_w1_hi);
+    prefetch_tmap(&tm_f_hi);
+    for (int s = 0; s < NX; ++s) { mbar_init(&x_full[s], 2 * PRODUCER_WARPS); mbar_init(&x_empty[s], 1); }
+    for (int s = 0; s < NH; ++s) { mbar_init(&h_full[s], 4); mbar_init(&h_empty[s], 1); }
+    for (int s = 0; s < p.nb; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    mbar_init(a1_full, 1); mbar_init(a1_empty, 8);
+    mbar_init(a3_full, 1); mbar_init(a3_empty, 8);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < N1; i += THREADS) sbias1[i] = p.bias1[i];
+  for (int i = threadIdx.x; i < N3; i += THREADS) sbiasf[i] = p.biasf[i];
+  if (warp == 1) tmem_alloc<2>(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== B-operand TMA producer ===========================
+    if (lane == 0) {
+      uint32_t bq = 0;
+      for (int ray = pair; ray < nrays; ray += npairs) {
+        for (int v = 0; v < 2; ++v) {
+          for (int kb = 0; kb < K1_STAGES; ++kb, ++bq) {                    // W1 K-slices
+            const int s = bq % p.nb;
+            mbar_wait(&b_empty[s], ((bq / p.nb) & 1) ^ 1);
+            uint8_t *st = bs + (size_t)s * C::B_STAGE;
+            if (leader) mbar_expect_tx(&b_full[s], (uint32_t)(N1C * C::W1_CHUNK * C::OPS * 2));
+            for (int c = 0; c < N1C; ++c) {
+              const int n0 = c * N1CH + (int)rank * (N1CH / 2);
+              tma_load_2d_pair(st + c * C::W1_CHUNK, &tm_w1_hi, &b_full[s], kb * KS, n0);
+              if (SPLIT == 3) tma_load_2d_pair(st + C::B_HALF + c * C::W1_CHUNK, &tm_w1_lo, &b_full[s], kb * KS, n0);
+            }
+          }
+          for (int q = 0; q < K3_STAGES; ++q, ++bq) {                       // F_v K-slices, epilogue order
+            const int s = bq % p.nb;
+            mbar_wait(&b_empty[s], ((bq / p.nb) & 1) ^ 1);
+            uint8_t *st = bs + (size_t)s * C::B_STAGE;
+            const int half = q & 1, cj = q >> 1, c = cj / 3, jj = cj - c * 3;
+            const int k0 = v * N1 + c * N1CH + half * (N1CH / 2) + jj * KS;
+            if (leader) mbar_expect_tx(&b_full[s], (uint32_t)(N3C * C::F_CHUNK * C::OPS * 2));
+            for (int e = 0; e < N3C; ++e) {
+              const int n0 = e * N3CH + (int)rank * (N3CH / 2);
+              tma_load_2d_pair(st + e * C::F_CHUNK, &tm_f_hi, &b_full[s], k0, n0);
+              if (SPLIT == 3) tma_load_2d_pair(st + C::B_HALF + e * C::F_CHUNK, &tm_f_lo, &b_full[s], k0, n0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer (leader CTA) ===========================
+    if (leader && lane == 0) {
+      const uint32_t idesc1 = make_idesc_bf16(128, N1CH), idesc3 = make_idesc_bf16(128, N3CH);
+      uint32_t bq = 0, xq = 0, hq = 0, av = 0, rq = 0;
+      for (int ray = pair; ray < nrays; ray += npairs, ++rq) {
+        for (int v = 0; v < 2; ++v, ++av) {
+          mbar_wait(a1_empty, (av & 1) ^ 1);                                 // acc1 drained
+          tc_fence_after();
+          for (int kb = 0; kb < K1_STAGES; ++kb, ++bq, ++xq) {
+            const int sb = bq % p.nb, sx = xq % NX;
+            mbar_wait(&x_full[sx], (xq / NX) & 1);
+            mbar_wait(&b_full[sb], (bq / p.nb) & 1);
+            tc_fence_after();
+            const uint32_t xa = smem_u32(xs + (size_t)sx * C::A_STAGE);
+            const uint32_t wb = smem_u32(bs + (size_t)sb * C::B_STAGE);
+            const int ksteps = kb == K1_STAGES - 1 ? 1 : 2;
+            for (int k = 0; k < ksteps; ++k) {
+              const uint32_t koff = (uint32_t)k * 32;
+              const uint32_t acc = (kb | k) ? 1u : 0u;
+              for (int c = 0; c < N1C; ++c) {
+                const uint32_t d = tmem_base + ACC1_COL + (uint32_t)(c * (N1CH / 2));
+                const uint32_t w = wb + (uint32_t)(c * C::W1_CHUNK) + koff;
+                umma_f16<2>(d, make_desc<64>(xa + koff), make_desc<64>(w), idesc1, acc);
+                if (SPLIT == 3) {
+                  umma_f16<2>(d, make_desc<64>(xa + C::A_HALF + koff), make_desc<64>(w), idesc1, 1u);
+                  umma_f16<2>(d, make_desc<64>(xa + koff), make_desc<64>(w + C::B_HALF), idesc1, 1u);
+                }
+              }
+            }
+            umma_commit_pair(&x_empty[sx], 0x3);
+            umma_commit_pair(&b_empty[sb], 0x3);
+          }
+          umma_commit_pair(a1_full, 0x3);
+          if (v == 0) { mbar_wait(a3_empty, (rq & 1) ^ 1); tc_fence_after(); }
+          for (int q = 0; q < K3_STAGES; ++q, ++bq, ++hq) {
+            const int sb = bq % p.nb, sh = hq % NH;
+            mbar_wait(&h_full[sh], (hq / NH) & 1);
+            mbar_wait(&b_full[sb], (bq / p.nb) & 1);
+            tc_fence_after();
+            const uint32_t ha = smem_u32(hs + (size_t)sh * C::A_STAGE);
+            const uint32_t wb = smem_u32(bs + (size_t)sb * C::B_STAGE);
+            for (int k = 0; k < 2; ++k) {
+              const uint32_t koff = (uint32_t)k * 32;
+              const uint32_t acc = (v | q | k) ? 1u : 0u;
+              for (int e = 0; e < N3C; ++e) {
+                const uint32_t d = tmem_base + ACC3_COL + (uint32_t)(e * (N3CH / 2));
+                const uint32_t w = wb + (uint32_t)(e * C::F_CHUNK) + koff;
+                umma_f16<2>(d, make_desc<64>(ha + koff), make_desc<64>(w), idesc3, acc);
+                if (SPLIT == 3) {
+                  umma_f16<2>(d, make_desc<64>(ha + C::A_HALF + koff), make_desc<64>(w), idesc3, 1u);
+                  umma_f16<2>(d, make_desc<64>(ha + koff), make_desc<64>(w + C::B_HALF), idesc3, 1u);
+                }
+              }
+            }
+            umma_commit_pair(&h_empty[sh], 0x3);
+            umma_commit_pair(&b_empty[sb], 0x3);
+          }
+        }
+        umma_commit_pair(a3_full, 0x3);
+      }
+    }
+  } else if (warp < 6) {
+    // =========================== epilogue warps (2..5) ===========================
+    const int sub = warp & 3;
+    const int row = (sub & 1) * 32 + lane;                 // 0..63
+    const int half = sub >> 1;                             // lanes 64..127 hold the upper half of each chunk
+    const uint32_t tlane = tmem_base + ((uint32_t)(sub * 32) << 16);
+    uint32_t av = 0, rq = 0, hi_count = 0;                 // hi_count: chunks this half has produced
+    for (int ray = pair; ray < nrays; ray += npairs, ++rq) {
+      for (int v = 0; v < 2; ++v, ++av) {
+        mbar_wait(a1_full, av & 1);
+        tc_fence_after();
+        for (int cj = 0; cj < 9; ++cj, ++hi_count) {
+          const int c = cj / 3, jj = cj - c * 3;
+          uint32_t r[32];
+          tmem_ld32(tlane + ACC1_COL + (uint32_t)(c * (N1CH / 2) + jj * KS), r);
+          tmem_ld_wait();
+          const uint32_t hq = hi_count * 2 + (uint32_t)half;                 // global H chunk index
+          const int sh = hq % NH;
+          mbar_wait(&h_empty[sh], ((hq / NH) & 1) ^ 1);
+          uint8_t *dst = hs + (size_t)sh * C::A_STAGE;
+          const int n0 = c * N1CH + half * (N1CH / 2) + jj * KS;
+#pragma unroll
+          for (int c16 = 0; c16 < 4; ++c16) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int n = c16 * 8 + i * 2;
+              float a = fmaxf(__uint_as_float(r[n]) + sbias1[n0 + n], 0.f);
+              float b = fmaxf(__uint_as_float(r[n + 1]) + sbias1[n0 + n + 1], 0.f);
+              split2(a, b, hi[i], lo[i]);
+            }
+            const uint32_t off = swz_offset<64>(row, c16);
+            *reinterpret_cast<uint4 *>(dst + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (SPLIT == 3) *reinterpret_cast<uint4 *>(dst + C::A_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&h_full[sh], 0);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(a1_empty, 0);
+      }
+      // ---- acc3 -> V (fp32) and relu(key pre-activation) (bf16 hi/lo) ----
+      mbar_wait(a3_full, rq & 1);
+      tc_fence_after();
+      const size_t grow = ((size_t)ray * 2 + rank) * ROWS + row;
+      for (int e = 0; e < N3C; ++e) {
+        for (int j0 = 0; j0 < N3CH / 2; j0 += 8) {
+          uint32_t r[8];
+          tmem_ld8(tlane + ACC3_COL + (uint32_t)(e * (N3CH / 2) + j0), r);
+          tmem_ld_wait();
+          const int n0 = e * N3CH + half * (N3CH / 2) + j0;                 // 0..415, multiple of 8
+          float vv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) vv[i] = __uint_as_float(r[i]) + sbiasf[n0 + i];
+          if (n0 < CAR_C_LAT) {
+            float *o = p.value + grow * CAR_C_LAT + n0;
+            *reinterpret_cast<float4 *>(o) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+            *reinterpret_cast<float4 *>(o + 4) = make_float4(vv[4], vv[5], vv[6], vv[7]);
+          } else {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split2(fmaxf(vv[2 * i], 0.f), fmaxf(vv[2 * i + 1], 0.f), hi[i], lo[i]);
+            const size_t o = grow * 128 + (n0 - CAR_C_LAT);
+            *reinterpret_cast<uint4 *>(p.kh_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (SPLIT == 3) *reinterpret_cast<uint4 *>(p.kh_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(a3_empty, 0);
+    }
+  } else {
+    // =========================== gather producers (warps 6..13) ===========================
+    const int pt = threadIdx.x - 6 * 32;                   // 0..255
+    const FT *f0 = reinterpret_cast<const FT *>(p.feat[0]);
+    const FT *f1 = reinterpret_cast<const FT *>(p.feat[1]);
+    const FT *f2 = reinterpret_cast<const FT *>(p.feat[2]);
+    uint32_t xq = 0;
+    for (int ray = pair; ray < nrays; ray += npairs) {
+      const int g = p.g0 + ray;
+      const int scene = g / p.R;
+      // ---- tap table for this ray's 64 samples: [row][level][own|cross] ----
+      asm volatile("bar.sync 1, 256;" ::: "memory");       // previous ray's stages are all written
+      if (pt < ROWS * 3) {
+        const int rr = pt / 3, lvl = pt - rr * 3;
+        const float *G = p.geom + (((size_t)ray * 2 + rank) * ROWS + rr) * CAR_GEOM_STRIDE;
+        const int h = lvl == 0 ? p.H / 4 : (lvl == 1 ? p.H / 2 : p.H);
+        const int w = lvl == 0 ? p.W / 4 : (lvl == 1 ? p.W / 2 : p.W);
+        taps[(rr * 3 + lvl) * 2 + 0] = make_taps(G[G_GX], G[G_GY], w, h, true);
+        taps[(rr * 3 + lvl) * 2 + 1] = make_taps(G[G_GXC], G[G_GYC], w, h, false);
+        if (lvl == 0) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) { tanhs[rr * 8 + i] = G[G_T0 + i]; tanhs[rr * 8 + 4 + i] = G[G_T1 + i]; }
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int v = 0; v < 2; ++v) {
+        const int oc = (v == (int)rank) ? 0 : 1;           // own line (border taps) or cross-view taps
+        for (int kb = 0; kb < K1_STAGES; ++kb, ++xq) {
+          const int sx = xq % NX;
+          mbar_wait(&x_empty[sx], ((xq / NX) & 1) ^ 1);
+          uint8_t *dst = xs + (size_t)sx * C::A_STAGE;
+          if (kb < K1_STAGES - 1) {
+            const int ch0 = kb * KS;
+            const int lvl = ch0 < 256 ? 0 : (ch0 < 512 ? 1 : 2);
+            const int coff = ch0 - (lvl == 0 ? 0 : (lvl == 1 ? 256 : 512));
+            const int Cc = lvl == 2 ? 64 : 256;
+            const int h = lvl == 0 ? p.H / 4 : (lvl == 1 ? p.H / 2 : p.H);
+            const int w = lvl == 0 ? p.W / 4 : (lvl == 1 ? p.W / 2 : p.W);
+            const FT *img = (lvl == 0 ? f0 : (lvl == 1 ? f1 : f2)) + (size_t)(scene * 2 + v) * h * w * Cc + coff;
+            if (sizeof(FT) == 4) {
+              // 64 rows x 8 groups of 4 channels; thread handles items pt and pt+256
+#pragma unroll
+              for (int it = 0; it < 2; ++it) {
+                const int item = pt + it * 256, rr = item >> 3, grp = item & 7;
+                const TapEntry t = taps[(rr * 3 + lvl) * 2 + oc];
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (t.off[k] >= 0) {
+                    const float4 x = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(img) + (size_t)t.off[k] * Cc + grp * 4));
+                    acc.x = fmaf(x.x, t.w[k], acc.x); acc.y = fmaf(x.y, t.w[k], acc.y);
+                    acc.z = fmaf(x.z, t.w[k], acc.z); acc.w = fmaf(x.w, t.w[k], acc.w);
+                  }
+                }
+                uint32_t h0, l0, h1, l1;
+                split2(acc.x, acc.y, h0, l0);
+                split2(acc.z, acc.w, h1, l1);
+                const uint32_t off = swz_offset<64>(rr, grp >> 1) + (uint32_t)((grp & 1) * 8);
+                *reinterpret_cast<uint2 *>(dst + off) = make_uint2(h0, h1);
+                if (SPLIT == 3) *reinterpret_cast<uint2 *>(dst + C::A_HALF + off) = make_uint2(l0, l1);
+              }
+            } else {
+              // bf16 maps: 64 rows x 4 groups of 8 channels, one item per thread
+              const int rr = pt >> 2, grp = pt & 3;
+              const TapEntry t = taps[(rr * 3 + lvl) * 2 + oc];
+              float a8[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) a8[i] = 0.f;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (t.off[k] >= 0) {
+                  const uint4 u = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint16_t *>(img) + (size_t)t.off[k] * Cc + grp * 8));
+                  const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    a8[2 * i] = fmaf(__uint_as_float(uu[i] << 16), t.w[k], a8[2 * i]);
+                    a8[2 * i + 1] = fmaf(__uint_as_float(uu[i] & 0xffff0000u), t.w[k], a8[2 * i + 1]);
+                  }
+                }
+              }
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) split2(a8[2 * i], a8[2 * i + 1], hi[i], lo[i]);
+              const uint32_t off = swz_offset<64>(rr, grp);
+              *reinterpret_cast<uint4 *>(dst + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              if (SPLIT == 3) *reinterpret_cast<uint4 *>(dst + C::A_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          } else {
+            // last stage: [tanh(pt_v / 5) (3) | zeros]; only the first 16 K-columns are multiplied
+            const int rr = pt >> 2, c16 = pt & 3;
+            uint32_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
+            if (c16 == 0) {
+              const float *T = tanhs + rr * 8 + v * 4;
+              split2(T[0], T[1], hi[0], lo[0]);
+              split2(T[2], 0.f, hi[1], lo[1]);
+            }
+            const uint32_t off = swz_offset<64>(rr, c16);
+            *reinterpret_cast<uint4 *>(dst + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (SPLIT == 3) *reinterpret_cast<uint4 *>(dst + C::A_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&x_full[sx], 0);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<2>(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+// Launch for rays [g0,g1) of the current chunk.  Returns 0 or an error code.
+int launch_fused_encode(const car_render_args &a, int g0, int g1, const float *geom, float *value,
+                        uint16_t *kh_hi, uint16_t *kh_lo, cudaStream_t st) {
+  const int split3 = a.precision == CAR_PREC_FP32_3XBF16;
+  const car_mat &W1 = a.weights.enc1, &F = a.weights.kv_fold;
+  if (a.P != ROWS || !F.hi || F.N != N3 || F.K != 2 * N1 || W1.N != N1 || W1.K != CAR_K_ENC) {
+    set_error("fused encode: unsupported configuration (P=%d)", a.P);
+    return -20;
+  }
+  CUtensorMap t1h, t1l, tfh, tfl;
+  int rc;
+  if ((rc = make_tmap_bf16(&t1h, W1.hi, W1.N, W1.K, W1.K, N1CH / 2, KS))) return rc;
+  if ((rc = make_tmap_bf16(&tfh, F.hi, F.N, F.K, F.K, N3CH / 2, KS))) return rc;
+  if (split3) {
+    if ((rc = make_tmap_bf16(&t1l, W1.lo, W1.N, W1.K, W1.K, N1CH / 2, KS))) return rc;
+    if ((rc = make_tmap_bf16(&tfl, F.lo, F.N, F.K, F.K, N3CH / 2, KS))) return rc;
+  } else { t1l = t1h; tfl = tfh; }
+  FusedParams p;
+  for (int i = 0; i < 3; ++i) p.feat[i] = a.feat[i];
+  p.H = a.H; p.W = a.W; p.R = a.R; p.g0 = g0; p.g1 = g1;
+  p.geom = geom; p.bias1 = W1.bias; p.biasf = F.bias;
+  p.value = value; p.kh_hi = kh_hi; p.kh_lo = kh_lo;
+  const int a_stage = ROWS * KS * 2 * (split3 ? 2 : 1);
+  const int b_stage = N1C * (N1CH / 2) * KS * 2 * (split3 ? 2 : 1);
+  const size_t fixed = (size_t)(NX + NH) * a_stage + ROWS * 3 * 2 * sizeof(TapEntry) + ROWS * 8 * 4 + (N1 + N3) * 4 +
+                       (2 * NX + 2 * NH + 2 * MAXB + 4) * 8 + 16 + 512;
+  int nb = (int)((227 * 1024 - fixed) / b_stage);
+  if (nb > MAXB) nb = MAXB;
+  if (nb < 2) { set_error("fused encode: not enough shared memory"); return -21; }
+  p.nb = nb;
+  const size_t smem = fixed + (size_t)nb * b_stage;
+  static int sms = 0;
+  if (!sms) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  int pairs = sms / 2;
+  if (pairs > g1 - g0) pairs = g1 - g0;
+  cudaError_t e = cudaSuccess;
+  prof_pre(CAR_ST_FUSED, st);
+#define CAR_LAUNCH(S, T)                                                                                    \
+  do {                                                                                                      \
+    e = cudaFuncSetAttribute(k_fused_encode<S, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+    if (e == cudaSuccess) k_fused_encode<S, T><<<pairs * 2, THREADS, smem, st>>>(t1h, t1l, tfh, tfl, p);      \
+  } while (0)
+  if (split3) { if (a.feat_bf16) CAR_LAUNCH(3, __nv_bfloat16); else CAR_LAUNCH(3, float); }
+  else { if (a.feat_bf16) CAR_LAUNCH(1, __nv_bfloat16); else CAR_LAUNCH(1, float); }
+#undef CAR_LAUNCH
+  prof_post(st);
+  if (e != cudaSuccess) { set_error("fused encode: %s", cudaGetErrorString(e)); return (int)e; }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("fused encode launch: %s", cudaGetErrorString(e)); return (int)e; }
+  count_launch();
+  return 0;
+}
+
+}  // namespace car

@@ -19,7 +19,6 @@ namespace {
 
 using namespace ptx;
 
-constexpr int BK = 64;
 constexpr int UMMA_K = 16;
 constexpr int THREADS = 192;
 constexpr int MAX_STAGES = 6;
@@ -32,7 +31,7 @@ struct PairParams {
   float *dump;     // optional raw TMEM dump: [pairs*2][128 lanes][N/2] (first tile of each pair)
 };
 
-template <int SPLIT>
+template <int SPLIT, int BK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 k_pair_gemm(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
             const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, PairParams p) {
@@ -115,10 +114,10 @@ k_pair_gemm(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             for (int c = 0; c < p.nch; ++c) {
               const uint32_t d = tmem_base + (uint32_t)(c * (p.NCH / 2));
               const uint32_t wb = sw + (uint32_t)c * wc_bytes + koff, wl = sw_lo + (uint32_t)c * wc_bytes + koff;
-              umma_f16<2>(d, make_desc<128>(sa + koff), make_desc<128>(wb), idesc, acc);
+              umma_f16<2>(d, make_desc<BK * 2>(sa + koff), make_desc<BK * 2>(wb), idesc, acc);
               if (SPLIT == 3) {
-                umma_f16<2>(d, make_desc<128>(sa_lo + koff), make_desc<128>(wb), idesc, 1u);
-                umma_f16<2>(d, make_desc<128>(sa + koff), make_desc<128>(wl), idesc, 1u);
+                umma_f16<2>(d, make_desc<BK * 2>(sa_lo + koff), make_desc<BK * 2>(wb), idesc, 1u);
+                umma_f16<2>(d, make_desc<BK * 2>(sa + koff), make_desc<BK * 2>(wl), idesc, 1u);
               }
             }
           }
@@ -217,8 +216,10 @@ int make_tmap_bf16(CUtensorMap *tm, const uint16_t *base, int rows, int K, int l
 
 extern "C" int car_gemm_pair_test(const uint16_t *a_hi, const uint16_t *a_lo, const uint16_t *w_hi,
                                   const uint16_t *w_lo, const float *bias, float *c, float *dump, int M, int N,
-                                  int K, int nch, int split3, int relu, int max_pairs, void *stream) {
+                                  int K, int nch, int split3, int relu, int max_pairs, int bk, void *stream) {
   using namespace car;
+  const int BK = bk;
+  if (BK != 64 && BK != 32) { set_error("pair gemm: bk must be 32 or 64"); return -12; }
   if (nch <= 0 || N % nch) { set_error("pair gemm: bad nch"); return -12; }
   int NCH = N / nch;
   if (NCH > 256 || NCH % 16 || K % 16 || N / 2 > 512) { set_error("pair gemm: unsupported N=%d nch=%d K=%d", N, nch, K); return -12; }
@@ -249,13 +250,14 @@ extern "C" int car_gemm_pair_test(const uint16_t *a_hi, const uint16_t *a_lo, co
   if (max_pairs > 0 && pairs > max_pairs) pairs = max_pairs;
   cudaError_t e;
   cudaStream_t st = (cudaStream_t)stream;
-  if (split3) {
-    e = cudaFuncSetAttribute(k_pair_gemm<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) k_pair_gemm<3><<<pairs * 2, THREADS, smem, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, p);
-  } else {
-    e = cudaFuncSetAttribute(k_pair_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) k_pair_gemm<1><<<pairs * 2, THREADS, smem, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, p);
-  }
+#define CAR_PG(S, B)                                                                                     \
+  do {                                                                                                   \
+    e = cudaFuncSetAttribute(k_pair_gemm<S, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+    if (e == cudaSuccess) k_pair_gemm<S, B><<<pairs * 2, THREADS, smem, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, p); \
+  } while (0)
+  if (split3) { if (BK == 64) CAR_PG(3, 64); else CAR_PG(3, 32); }
+  else { if (BK == 64) CAR_PG(1, 64); else CAR_PG(1, 32); }
+#undef CAR_PG
   if (e != cudaSuccess) { set_error("pair gemm: %s", cudaGetErrorString(e)); return (int)e; }
   e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("pair gemm launch: %s", cudaGetErrorString(e)); return (int)e; }

@@ -103,6 +103,7 @@ class CrossAttentionRenderer(nn.Module):
         self.feature_dtype = None            # None: fp32 for fp32*, bf16 for bf16
         self.pixel_val_to_cpu = True         # reference returns pixel_val on the host (models.py:570)
         self.chunk_rays = None
+        self.use_fused = os.environ.get("CAR_FUSED", "1") != "0"   # fused gather+encode kernel (P == 64)
         self._wcache = None
         self._fcache = None
         self._ws = None
@@ -242,12 +243,16 @@ class CrossAttentionRenderer(nn.Module):
             shapes = {"geom": (rows, _lib.GEOM_STRIDE), "x": (rows, 2, _lib.K_ENC), "interp": (rows, 576),
                       "value": (rows, 288), "key": (rows, 128), "q1": (rows, 128), "q2": (rows, 128),
                       "zfinal": (g1 - g0, 288)}
+            want = debug_taps.pop("_keys", None)
             for k, shp in shapes.items():
                 if k == "x" and prec != _lib.PREC_FP32_SIMT:
+                    continue
+                if want is not None and k not in want:
                     continue
                 debug_taps[k] = torch.zeros(*shp, device=dev)
                 setattr(a.debug, k, debug_taps[k].data_ptr())
         a.stream = torch.cuda.current_stream(dev).cuda_stream
+        a.use_fused = int(self.use_fused)
         with torch.cuda.device(dev):
             _lib.check(lib.car_render_forward(a), "car_render_forward")
         self.last_launch_count = lib.car_last_launch_count()

@@ -70,11 +70,19 @@ class PackedWeights:
             self.m[f"phi_fc0{i}"] = P(g(f"phi.blocks.{i}.fc_0.weight"), g(f"phi.blocks.{i}.fc_0.bias"))
             self.m[f"phi_fc1{i}"] = P(g(f"phi.blocks.{i}.fc_1.weight"), g(f"phi.blocks.{i}.fc_1.bias"))
         self.m["phi_out"] = P(g("phi.lin_out.weight"), g("phi.lin_out.bias"))
+        # fold query_encode_latent_2 into [latent_value ; key_map] (float64 product, rounded once)
+        w2 = g("query_encode_latent_2.weight").reshape(288, 576).double()
+        b2 = g("query_encode_latent_2.bias").double()
+        w3 = torch.cat([g("latent_value.weight").reshape(288, 576), g("key_map.weight").reshape(128, 576)], 0).double()
+        b3 = torch.cat([g("latent_value.bias"), g("key_map.bias")], 0).double()
+        fold = torch.cat([w3[:, :288] @ w2, w3[:, 288:] @ w2], dim=1)            # (416, 1152)
+        bfold = w3 @ torch.cat([b2, b2]) + b3
+        self.m["kv_fold"] = P(fold.float(), bfold.float())
 
     def c_struct(self):
         w = _lib.car_weights()
         for name in ("enc1", "enc2", "value", "key1", "key2", "qry1", "qry2", "rep1_loc",
-                     "rep1_g", "rep2", "enc_lat", "phi_in", "phi_out"):
+                     "rep1_g", "rep2", "enc_lat", "phi_in", "phi_out", "kv_fold"):
             setattr(w, name, self.m[name].c_struct())
         for i in range(3):
             w.phi_z[i] = self.m[f"phi_z{i}"].c_struct()

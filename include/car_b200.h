@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CAR_ABI_VERSION 3
+#define CAR_ABI_VERSION 4
 
 /* Arithmetic of the per-sample MLP GEMMs (everything else is fp32/fp64). */
 enum car_precision {
@@ -85,6 +85,11 @@ typedef struct car_weights {
   car_mat phi_fc0[3];/* phi.blocks.i.fc_0        N=128 K=128                         */
   car_mat phi_fc1[3];/* phi.blocks.i.fc_1        N=128 K=128                         */
   car_mat phi_out;   /* phi.lin_out              N=3   K=128                         */
+  /* [latent_value ; key_map] composed with query_encode_latent_2 (no non-linearity lies
+   * between them, models.py:333-344,487-491):  F[:, v*576:(v+1)*576] = W3[:, v*288:(v+1)*288] @ W2,
+   * bias = W3 @ [b2;b2] + [b_value; b_key].  Rows 0..287 -> V, rows 288..415 -> key_map pre-ReLU.
+   * Used by the fused kernel (tensor-core precisions, P == 64).  N=416 K=1152. */
+  car_mat kv_fold;
 } car_weights;
 
 /* ------------------------------------------------------------------------
@@ -138,6 +143,7 @@ typedef struct car_render_args {
   size_t workspace_bytes;
   car_debug debug;                /* all-NULL in production                                  */
   void *stream;                   /* cudaStream_t                                            */
+  int32_t use_fused;              /* 1: fused gather+encode kernel when eligible (P == 64)   */
 } car_render_args;
 
 /* Rays are processed in chunks of `chunk_rays`; workspace scales with the chunk. */
@@ -154,7 +160,7 @@ int car_last_launch_count(void);
  * ms[0..n) / launches[0..n) (HOST pointers) and stops recording. */
 enum car_stage { CAR_ST_RAYSETUP = 0, CAR_ST_SAMPLE_GEOM, CAR_ST_GATHER, CAR_ST_GEMM_ENC1,
                  CAR_ST_GEMM_ENC2, CAR_ST_GEMM_KV, CAR_ST_GEMM_SMALL, CAR_ST_ATTENTION,
-                 CAR_ST_PHI, CAR_ST_PACK, CAR_ST_FUSED, CAR_ST_COUNT };
+                 CAR_ST_PHI, CAR_ST_PACK, CAR_ST_FUSED, CAR_ST_COUNT };  /* FUSED = gather+enc1+enc2+kv in one kernel */
 int car_profile_begin(void);
 int car_profile_end(float *ms, int *launches, int n);
 
@@ -169,7 +175,7 @@ int car_gemm_umma_test(const uint16_t *a_hi, const uint16_t *a_lo, const uint16_
  * receives the raw TMEM image [pairs*2][128 lanes][N/2] of each pair's first tile. */
 int car_gemm_pair_test(const uint16_t *a_hi, const uint16_t *a_lo, const uint16_t *w_hi,
                        const uint16_t *w_lo, const float *bias, float *c, float *dump, int M, int N,
-                       int K, int nch, int split3, int relu, int max_pairs, void *stream);
+                       int K, int nch, int split3, int relu, int max_pairs, int bk /*32|64*/, void *stream);
 
 #ifdef __cplusplus
 }

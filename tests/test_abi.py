@@ -47,9 +47,10 @@ def test_struct_layout_matches_c(tmp_path):
 int main(void) {
   printf("%zu %zu %zu %zu %zu\\n", sizeof(car_mat), sizeof(car_weights), sizeof(car_cameras),
          sizeof(car_debug), sizeof(car_render_args));
-  printf("%zu %zu %zu %zu %zu %zu\\n", offsetof(car_render_args, feat), offsetof(car_render_args, weights),
+  printf("%zu %zu %zu %zu %zu %zu %zu\\n", offsetof(car_render_args, feat), offsetof(car_render_args, weights),
          offsetof(car_render_args, cams), offsetof(car_render_args, uv),
-         offsetof(car_render_args, workspace_bytes), offsetof(car_render_args, stream));
+         offsetof(car_render_args, workspace_bytes), offsetof(car_render_args, stream),
+         offsetof(car_render_args, use_fused));
   return 0;
 }''')
     exe = tmp_path / "probe"
@@ -61,7 +62,7 @@ int main(void) {
     assert sizes == [C.sizeof(_lib.car_mat), C.sizeof(_lib.car_weights), C.sizeof(_lib.car_cameras),
                      C.sizeof(_lib.car_debug), C.sizeof(A)]
     assert offs == [A.feat.offset, A.weights.offset, A.cams.offset, A.uv.offset,
-                    A.workspace_bytes.offset, A.stream.offset]
+                    A.workspace_bytes.offset, A.stream.offset, A.use_fused.offset]
 
 
 def test_sizes_and_argument_errors(lib):

@@ -42,7 +42,7 @@ def test_gemm_umma(M, N, K, split3):
     assert err < tol, err
 
 
-def _pair_call(lib, A, W, bias, nch, split3, relu=1, max_pairs=0, dump=False):
+def _pair_call(lib, A, W, bias, nch, split3, relu=1, max_pairs=0, dump=False, bk=64):
     M, K = A.shape
     N = W.shape[0]
     ah, al = split(A)
@@ -53,7 +53,7 @@ def _pair_call(lib, A, W, bias, nch, split3, relu=1, max_pairs=0, dump=False):
     rc = lib.car_gemm_pair_test(ah.data_ptr(), al.data_ptr() if split3 else None, wh.data_ptr(),
                                 wl.data_ptr() if split3 else None, bias.data_ptr() if bias is not None else None,
                                 C.data_ptr(), D.data_ptr() if dump else None, M, N, K, nch, split3, relu,
-                                max_pairs, torch.cuda.current_stream().cuda_stream)
+                                max_pairs, bk, torch.cuda.current_stream().cuda_stream)
     assert rc == 0, lib.car_last_error()
     torch.cuda.synchronize()
     return C, D, (ah, wh)
@@ -81,13 +81,14 @@ def test_pair_gemm_layout_probe():
 @pytest.mark.parametrize("M,N,K,nch", [(128, 192, 64, 1), (300, 576, 592, 3), (5000, 576, 592, 3),
                                        (1000, 416, 576, 2), (1000, 128, 128, 1), (20000, 128, 16, 1)])
 @pytest.mark.parametrize("split3", [0, 1])
-def test_pair_gemm(M, N, K, nch, split3):
+@pytest.mark.parametrize("bk", [64, 32])
+def test_pair_gemm(M, N, K, nch, split3, bk):
     lib = _lib.load()
     g = torch.Generator().manual_seed(M * 7 + N + K)
     A = torch.randn(M, K, generator=g).cuda()
     W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
     bias = torch.randn(N, generator=g).cuda()
-    C, _, (ah, wh) = _pair_call(lib, A, W, bias, nch, split3)
+    C, _, (ah, wh) = _pair_call(lib, A, W, bias, nch, split3, bk=bk)
     if split3:
         ref = torch.relu(A.double() @ W.double().T + bias.double()); tol = 3e-5
     else:

@@ -290,3 +290,37 @@ def test_forward_wrapper_pose_algebra_on_gpu():
     assert rel_err(cpu(out["rgb"]), rec["out_rgb"]) < 5e-3
     assert torch.equal(cpu(out["valid_mask"]), rec["out_valid_mask"])
     assert out["pixel_val"].device.type == "cpu" and out["z"] is not None and "uv" in out
+
+
+# ---------------------------------------------------------------------------------------
+# fused gather+encode kernel (CTA pair, P == 64) against the unfused tensor-core pipeline
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision,feat", [("fp32", None), ("bf16", None), ("bf16", "fp32"), ("fp32", "bf16")])
+def test_fused_encode_matches_unfused(precision, feat):
+    b, H, Ht, P = 2, 64, 20, 64
+    inp = synthetic.make_inputs(b, H, Ht, seed=33, mode="mixed")
+    z = synthetic.make_features(b, H, seed=33)
+    sd = synthetic.make_state_dict(seed=33, peaky=True)
+    cams = orc.prepare_cameras(inp)
+    interval = torch.linspace(0, 1, P)
+    outs, taps = {}, {}
+    for fused in (False, True):
+        model = make_model(sd, P, H, precision=precision, use_fused=fused, feature_dtype=feat)
+        taps[fused] = {"_keys": ("value", "key", "q1", "q2", "zfinal")}
+        outs[fused] = run_cuda(model, inp, z, cams=cams, interval=interval, debug_taps=taps[fused])
+    # same arithmetic up to accumulation order and the folded enc2∘[value;key] weights
+    tol = 2e-4 if precision == "fp32" else 3e-2
+    for k in ("value", "key", "zfinal"):
+        a, r = cpu(taps[True][k]), cpu(taps[False][k])
+        assert torch.isfinite(a).all(), k
+        err = float((a - r).abs().max() / r.abs().max())
+        assert err < tol, (k, err)
+    for k in ("q1",):
+        assert torch.equal(cpu(taps[True][k]), cpu(taps[False][k]))
+    assert rel_err(cpu(outs[True]["rgb"]), cpu(outs[False]["rgb"])) < (2e-4 if precision == "fp32" else 5e-2)
+    if precision == "fp32":
+        with torch.no_grad():
+            ref = orc.render(sd, inp, z, H, H, P, interval=interval, cams=cams)
+        assert rel_err(cpu(outs[True]["rgb"]), ref["rgb"]) < 1e-4
+        assert torch.allclose(cpu(taps[True]["value"]), _rows(ref["_I"]["value"], b, P), rtol=2e-4,
+                              atol=2e-4 * float(ref["_I"]["value"].abs().max()))
