@@ -318,7 +318,7 @@ def test_fused_encode_matches_unfused(precision, feat):
     for k in ("q1",):
         assert torch.equal(cpu(taps[True][k]), cpu(taps[False][k]))
     assert rel_err(cpu(outs[True]["rgb"]), cpu(outs[False]["rgb"])) < (2e-4 if precision == "fp32" else 5e-2)
-    if precision == "fp32":
+    if precision == "fp32" and feat is None:         # fp32 maps + 3xbf16 GEMMs: the 1e-4 bar
         with torch.no_grad():
             ref = orc.render(sd, inp, z, H, H, P, interval=interval, cams=cams)
         assert rel_err(cpu(outs[True]["rgb"]), ref["rgb"]) < 1e-4
