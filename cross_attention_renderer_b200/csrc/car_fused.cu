@@ -112,9 +112,9 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
   uint8_t *xs = smem;                                       // NX x A_STAGE
   uint8_t *hs = xs + NX * C::A_STAGE;                       // NH x A_STAGE
   uint8_t *bs = hs + NH * C::A_STAGE;                       // nb x B_STAGE
-  TapEntry *taps = reinterpret_cast<TapEntry *>(bs + (size_t)p.nb * C::B_STAGE);   // [64][3][2]
-  float *tanhs = reinterpret_cast<float *>(taps + ROWS * 3 * 2);                   // [64][8]
-  float *sbias1 = tanhs + ROWS * 8;                                                // [576]
+  TapEntry *taps = reinterpret_cast<TapEntry *>(bs + (size_t)p.nb * C::B_STAGE);   // [2 buffers][64][3][2]
+  float *tanhs = reinterpret_cast<float *>(taps + 2 * ROWS * 3 * 2);               // [2][64][8]
+  float *sbias1 = tanhs + 2 * ROWS * 8;                                                // [576]
   float *sbiasf = sbias1 + N1;                                                     // [416]
   uint64_t *bars = reinterpret_cast<uint64_t *>(sbiasf + N3);
   uint64_t *x_full = bars, *x_empty = x_full + NX;
@@ -133,7 +133,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_w1_hi);
     prefetch_tmap(&tm_f_hi);
-    for (int s = 0; s < NX; ++s) { mbar_init(&x_full[s], 2 * PRODUCER_WARPS); mbar_init(&x_empty[s], 1); }
+    for (int s = 0; s < NX; ++s) { mbar_init(&x_full[s], 4);   /* 2 warps of the owning group x 2 CTAs */ mbar_init(&x_empty[s], 1); }
     for (int s = 0; s < NH; ++s) { mbar_init(&h_full[s], 4); mbar_init(&h_empty[s], 1); }
     for (int s = 0; s < p.nb; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     mbar_init(a1_full, 1); mbar_init(a1_empty, 8);
@@ -320,57 +320,79 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
     }
   } else {
     // =========================== gather producers (warps 6..13) ===========================
+    // Four groups of two warps; group gi owns X-ring slot gi and produces the K-stages with
+    // xq % 4 == gi, so four stages are in flight per CTA.  Each thread issues all tap loads of
+    // four (row, channel-group) items before consuming them (memory-level parallelism).
     const int pt = threadIdx.x - 6 * 32;                   // 0..255
-    const FT *f0 = reinterpret_cast<const FT *>(p.feat[0]);
-    const FT *f1 = reinterpret_cast<const FT *>(p.feat[1]);
-    const FT *f2 = reinterpret_cast<const FT *>(p.feat[2]);
-    uint32_t xq = 0;
-    for (int ray = pair; ray < nrays; ray += npairs) {
-      const int g = p.g0 + ray;
-      const int scene = g / p.R;
-      // ---- tap table for this ray's 64 samples: [row][level][own|cross] ----
-      asm volatile("bar.sync 1, 256;" ::: "memory");       // previous ray's stages are all written
+    const int gi = pt >> 6, gt = pt & 63;                  // group, thread within group
+    const FT *fbase[3] = {reinterpret_cast<const FT *>(p.feat[0]), reinterpret_cast<const FT *>(p.feat[1]),
+                          reinterpret_cast<const FT *>(p.feat[2])};
+    auto build_taps = [&](int ray_l, int buf) {
       if (pt < ROWS * 3) {
         const int rr = pt / 3, lvl = pt - rr * 3;
-        const float *G = p.geom + (((size_t)ray * 2 + rank) * ROWS + rr) * CAR_GEOM_STRIDE;
+        const float *G = p.geom + (((size_t)ray_l * 2 + rank) * ROWS + rr) * CAR_GEOM_STRIDE;
         const int h = lvl == 0 ? p.H / 4 : (lvl == 1 ? p.H / 2 : p.H);
         const int w = lvl == 0 ? p.W / 4 : (lvl == 1 ? p.W / 2 : p.W);
-        taps[(rr * 3 + lvl) * 2 + 0] = make_taps(G[G_GX], G[G_GY], w, h, true);
-        taps[(rr * 3 + lvl) * 2 + 1] = make_taps(G[G_GXC], G[G_GYC], w, h, false);
+        TapEntry *tb = taps + buf * (ROWS * 3 * 2);
+        tb[(rr * 3 + lvl) * 2 + 0] = make_taps(G[G_GX], G[G_GY], w, h, true);
+        tb[(rr * 3 + lvl) * 2 + 1] = make_taps(G[G_GXC], G[G_GYC], w, h, false);
         if (lvl == 0) {
+          float *th = tanhs + buf * (ROWS * 8);
 #pragma unroll
-          for (int i = 0; i < 3; ++i) { tanhs[rr * 8 + i] = G[G_T0 + i]; tanhs[rr * 8 + 4 + i] = G[G_T1 + i]; }
+          for (int i = 0; i < 3; ++i) { th[rr * 8 + i] = G[G_T0 + i]; th[rr * 8 + 4 + i] = G[G_T1 + i]; }
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int v = 0; v < 2; ++v) {
+    };
+    if (pair < nrays) build_taps(pair, 0);
+    int it_ray = 0;
+    for (int ray = pair; ray < nrays; ray += npairs, ++it_ray) {
+      const int scene = (p.g0 + ray) / p.R;
+      const int buf = it_ray & 1;
+      asm volatile("bar.sync 1, 256;" ::: "memory");       // table[buf] complete; table[buf^1] no longer read
+      if (ray + npairs < nrays) build_taps(ray + npairs, buf ^ 1);
+      const TapEntry *tb = taps + buf * (ROWS * 3 * 2);
+      const float *th = tanhs + buf * (ROWS * 8);
+      // this ray's 38 stages are numbered s = v*19 + kb; the group takes those with (xq0 + s) % 4 == gi
+      const uint32_t xq0 = (uint32_t)it_ray * (2 * K1_STAGES);
+      for (int sidx = (int)((gi + 4 - (xq0 & 3)) & 3); sidx < 2 * K1_STAGES; sidx += 4) {
+        const uint32_t xq = xq0 + (uint32_t)sidx;
+        const int v = sidx >= K1_STAGES ? 1 : 0, kb = sidx - v * K1_STAGES;
         const int oc = (v == (int)rank) ? 0 : 1;           // own line (border taps) or cross-view taps
-        for (int kb = 0; kb < K1_STAGES; ++kb, ++xq) {
-          const int sx = xq % NX;
-          mbar_wait(&x_empty[sx], ((xq / NX) & 1) ^ 1);
-          uint8_t *dst = xs + (size_t)sx * C::A_STAGE;
-          if (kb < K1_STAGES - 1) {
-            const int ch0 = kb * KS;
-            const int lvl = ch0 < 256 ? 0 : (ch0 < 512 ? 1 : 2);
-            const int coff = ch0 - (lvl == 0 ? 0 : (lvl == 1 ? 256 : 512));
-            const int Cc = lvl == 2 ? 64 : 256;
-            const int h = lvl == 0 ? p.H / 4 : (lvl == 1 ? p.H / 2 : p.H);
-            const int w = lvl == 0 ? p.W / 4 : (lvl == 1 ? p.W / 2 : p.W);
-            const FT *img = (lvl == 0 ? f0 : (lvl == 1 ? f1 : f2)) + (size_t)(scene * 2 + v) * h * w * Cc + coff;
-            if (sizeof(FT) == 4) {
-              // 64 rows x 8 groups of 4 channels; thread handles items pt and pt+256
+        mbar_wait(&x_empty[gi], ((xq / NX) & 1) ^ 1);
+        uint8_t *dst = xs + (size_t)gi * C::A_STAGE;
+        if (kb < K1_STAGES - 1) {
+          const int ch0 = kb * KS;
+          const int lvl = ch0 < 256 ? 0 : (ch0 < 512 ? 1 : 2);
+          const int coff = ch0 - (lvl == 0 ? 0 : (lvl == 1 ? 256 : 512));
+          const int Cc = lvl == 2 ? 64 : 256;
+          const int h = lvl == 0 ? p.H / 4 : (lvl == 1 ? p.H / 2 : p.H);
+          const int w = lvl == 0 ? p.W / 4 : (lvl == 1 ? p.W / 2 : p.W);
+          const FT *img = fbase[lvl] + (size_t)(scene * 2 + v) * h * w * Cc + coff;
+          if (sizeof(FT) == 4) {
+            // 64 rows x 8 groups of 4 channels = 512 items; thread handles items gt + 64*i
 #pragma unroll
-              for (int it = 0; it < 2; ++it) {
-                const int item = pt + it * 256, rr = item >> 3, grp = item & 7;
-                const TapEntry t = taps[(rr * 3 + lvl) * 2 + oc];
+            for (int round = 0; round < 2; ++round) {
+              float4 x[4][4];
+              float wt[4][4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int item = gt + 64 * (round * 4 + i), rr = item >> 3, grp = item & 7;
+                const TapEntry t = tb[(rr * 3 + lvl) * 2 + oc];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  wt[i][k] = t.off[k] >= 0 ? t.w[k] : 0.f;
+                  const int o = t.off[k] >= 0 ? t.off[k] : 0;
+                  x[i][k] = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(img) + (size_t)o * Cc + grp * 4));
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int item = gt + 64 * (round * 4 + i), rr = item >> 3, grp = item & 7;
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  if (t.off[k] >= 0) {
-                    const float4 x = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(img) + (size_t)t.off[k] * Cc + grp * 4));
-                    acc.x = fmaf(x.x, t.w[k], acc.x); acc.y = fmaf(x.y, t.w[k], acc.y);
-                    acc.z = fmaf(x.z, t.w[k], acc.z); acc.w = fmaf(x.w, t.w[k], acc.w);
-                  }
+                  acc.x = fmaf(x[i][k].x, wt[i][k], acc.x); acc.y = fmaf(x[i][k].y, wt[i][k], acc.y);
+                  acc.z = fmaf(x[i][k].z, wt[i][k], acc.z); acc.w = fmaf(x[i][k].w, wt[i][k], acc.w);
                 }
                 uint32_t h0, l0, h1, l1;
                 split2(acc.x, acc.y, h0, l0);
@@ -379,38 +401,53 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
                 *reinterpret_cast<uint2 *>(dst + off) = make_uint2(h0, h1);
                 if (SPLIT == 3) *reinterpret_cast<uint2 *>(dst + C::A_HALF + off) = make_uint2(l0, l1);
               }
-            } else {
-              // bf16 maps: 64 rows x 4 groups of 8 channels, one item per thread
-              const int rr = pt >> 2, grp = pt & 3;
-              const TapEntry t = taps[(rr * 3 + lvl) * 2 + oc];
-              float a8[8];
+            }
+          } else {
+            // bf16 maps: 64 rows x 4 groups of 8 channels = 256 items; thread handles gt + 64*i
+            uint4 x[4][4];
+            float wt[4][4];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) a8[i] = 0.f;
+            for (int i = 0; i < 4; ++i) {
+              const int item = gt + 64 * i, rr = item >> 2, grp = item & 3;
+              const TapEntry t = tb[(rr * 3 + lvl) * 2 + oc];
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                if (t.off[k] >= 0) {
-                  const uint4 u = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint16_t *>(img) + (size_t)t.off[k] * Cc + grp * 8));
-                  const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+                wt[i][k] = t.off[k] >= 0 ? t.w[k] : 0.f;
+                const int o = t.off[k] >= 0 ? t.off[k] : 0;
+                x[i][k] = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint16_t *>(img) + (size_t)o * Cc + grp * 8));
+              }
+            }
 #pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    a8[2 * i] = fmaf(__uint_as_float(uu[i] << 16), t.w[k], a8[2 * i]);
-                    a8[2 * i + 1] = fmaf(__uint_as_float(uu[i] & 0xffff0000u), t.w[k], a8[2 * i + 1]);
-                  }
+            for (int i = 0; i < 4; ++i) {
+              const int item = gt + 64 * i, rr = item >> 2, grp = item & 3;
+              float a8[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) a8[j] = 0.f;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t uu[4] = {x[i][k].x, x[i][k].y, x[i][k].z, x[i][k].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  a8[2 * j] = fmaf(__uint_as_float(uu[j] << 16), wt[i][k], a8[2 * j]);
+                  a8[2 * j + 1] = fmaf(__uint_as_float(uu[j] & 0xffff0000u), wt[i][k], a8[2 * j + 1]);
                 }
               }
               uint32_t hi[4], lo[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) split2(a8[2 * i], a8[2 * i + 1], hi[i], lo[i]);
+              for (int j = 0; j < 4; ++j) split2(a8[2 * j], a8[2 * j + 1], hi[j], lo[j]);
               const uint32_t off = swz_offset<64>(rr, grp);
               *reinterpret_cast<uint4 *>(dst + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               if (SPLIT == 3) *reinterpret_cast<uint4 *>(dst + C::A_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
-          } else {
-            // last stage: [tanh(pt_v / 5) (3) | zeros]; only the first 16 K-columns are multiplied
-            const int rr = pt >> 2, c16 = pt & 3;
+          }
+        } else {
+          // last stage: [tanh(pt_v / 5) (3) | zeros]; only the first 16 K-columns are multiplied
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int item = gt + 64 * i, rr = item >> 2, c16 = item & 3;
             uint32_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
             if (c16 == 0) {
-              const float *T = tanhs + rr * 8 + v * 4;
+              const float *T = th + rr * 8 + v * 4;
               split2(T[0], T[1], hi[0], lo[0]);
               split2(T[2], 0.f, hi[1], lo[1]);
             }
@@ -418,10 +455,10 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
             *reinterpret_cast<uint4 *>(dst + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             if (SPLIT == 3) *reinterpret_cast<uint4 *>(dst + C::A_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(&x_full[sx], 0);
         }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&x_full[gi], 0);
       }
     }
   }
@@ -460,7 +497,7 @@ int launch_fused_encode(const car_render_args &a, int g0, int g1, const float *g
   p.value = value; p.kh_hi = kh_hi; p.kh_lo = kh_lo;
   const int a_stage = ROWS * KS * 2 * (split3 ? 2 : 1);
   const int b_stage = N1C * (N1CH / 2) * KS * 2 * (split3 ? 2 : 1);
-  const size_t fixed = (size_t)(NX + NH) * a_stage + ROWS * 3 * 2 * sizeof(TapEntry) + ROWS * 8 * 4 + (N1 + N3) * 4 +
+  const size_t fixed = (size_t)(NX + NH) * a_stage + 2 * (ROWS * 3 * 2 * sizeof(TapEntry) + ROWS * 8 * 4) + (N1 + N3) * 4 +
                        (2 * NX + 2 * NH + 2 * MAXB + 4) * 8 + 16 + 512;
   int nb = (int)((227 * 1024 - fixed) / b_stage);
   if (nb > MAXB) nb = MAXB;
