@@ -26,6 +26,7 @@
 #include "car_umma.cuh"
 
 namespace car {
+extern unsigned long long *g_fused_stats;
 int make_tmap_bf16(CUtensorMap *tm, const uint16_t *base, int rows, int K, int ld, int box_rows, int box_k);
 
 namespace {
@@ -45,6 +46,20 @@ constexpr int MAXB = 6;
 
 struct TapEntry { int off[4]; float w[4]; };              // 32 bytes
 
+// Optional stall accounting (bench/diagnostics): cycles spent in each barrier wait, summed over
+// pair 0's leader roles.  Index map: 0 mma:a1_empty 1 mma:x_full 2 mma:b_full(gemm1) 3 mma:a3_empty
+// 4 mma:h_full 5 mma:b_full(gemm3) 6 mma:total | 8 epi:a1_full 9 epi:h_empty 10 epi:a3_full 11 epi:total
+// | 12 prod:x_empty 13 prod:total 14 prod:barrier | 16 tma:b_empty 17 tma:total
+__device__ __forceinline__ void timed_wait(uint64_t *bar, uint32_t parity, unsigned long long *st, int idx) {
+  if (st) {
+    long long t0 = clock64();
+    mbar_wait(bar, parity);
+    st[idx] += (unsigned long long)(clock64() - t0);
+  } else {
+    mbar_wait(bar, parity);
+  }
+}
+
 struct FusedParams {
   const void *feat[3];
   int H, W, R, g0, g1;
@@ -54,6 +69,7 @@ struct FusedParams {
   float *value;                        // (rows,288) fp32
   uint16_t *kh_hi, *kh_lo;             // (rows,128) bf16: relu(key_map)
   int nb;                              // B ring depth
+  unsigned long long *stats;           // optional [32] stall counters (see timed_wait), else null
 };
 
 template <int SPLIT> struct Cfg {
@@ -129,6 +145,9 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int nrays = p.g1 - p.g0;
+  unsigned long long lst[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long *st = (p.stats && pair == 0 && leader) ? lst : nullptr;
+  const long long t_begin = clock64();
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_w1_hi);
@@ -157,7 +176,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
         for (int v = 0; v < 2; ++v) {
           for (int kb = 0; kb < K1_STAGES; ++kb, ++bq) {                    // W1 K-slices
             const int s = bq % p.nb;
-            mbar_wait(&b_empty[s], ((bq / p.nb) & 1) ^ 1);
+            timed_wait(&b_empty[s], ((bq / p.nb) & 1) ^ 1, st, 0);
             uint8_t *st = bs + (size_t)s * C::B_STAGE;
             if (leader) mbar_expect_tx(&b_full[s], (uint32_t)(N1C * C::W1_CHUNK * C::OPS * 2));
             for (int c = 0; c < N1C; ++c) {
@@ -168,7 +187,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
           }
           for (int q = 0; q < K3_STAGES; ++q, ++bq) {                       // F_v K-slices, epilogue order
             const int s = bq % p.nb;
-            mbar_wait(&b_empty[s], ((bq / p.nb) & 1) ^ 1);
+            timed_wait(&b_empty[s], ((bq / p.nb) & 1) ^ 1, st, 0);
             uint8_t *st = bs + (size_t)s * C::B_STAGE;
             const int half = q & 1, cj = q >> 1, c = cj / 3, jj = cj - c * 3;
             const int k0 = v * N1 + c * N1CH + half * (N1CH / 2) + jj * KS;
@@ -189,12 +208,12 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
       uint32_t bq = 0, xq = 0, hq = 0, av = 0, rq = 0;
       for (int ray = pair; ray < nrays; ray += npairs, ++rq) {
         for (int v = 0; v < 2; ++v, ++av) {
-          mbar_wait(a1_empty, (av & 1) ^ 1);                                 // acc1 drained
+          timed_wait(a1_empty, (av & 1) ^ 1, st, 0);                         // acc1 drained
           tc_fence_after();
           for (int kb = 0; kb < K1_STAGES; ++kb, ++bq, ++xq) {
             const int sb = bq % p.nb, sx = xq % NX;
-            mbar_wait(&x_full[sx], (xq / NX) & 1);
-            mbar_wait(&b_full[sb], (bq / p.nb) & 1);
+            timed_wait(&x_full[sx], (xq / NX) & 1, st, 1);
+            timed_wait(&b_full[sb], (bq / p.nb) & 1, st, 2);
             tc_fence_after();
             const uint32_t xa = smem_u32(xs + (size_t)sx * C::A_STAGE);
             const uint32_t wb = smem_u32(bs + (size_t)sb * C::B_STAGE);
@@ -216,11 +235,11 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
             umma_commit_pair(&b_empty[sb], 0x3);
           }
           umma_commit_pair(a1_full, 0x3);
-          if (v == 0) { mbar_wait(a3_empty, (rq & 1) ^ 1); tc_fence_after(); }
+          if (v == 0) { timed_wait(a3_empty, (rq & 1) ^ 1, st, 3); tc_fence_after(); }
           for (int q = 0; q < K3_STAGES; ++q, ++bq, ++hq) {
             const int sb = bq % p.nb, sh = hq % NH;
-            mbar_wait(&h_full[sh], (hq / NH) & 1);
-            mbar_wait(&b_full[sb], (bq / p.nb) & 1);
+            timed_wait(&h_full[sh], (hq / NH) & 1, st, 4);
+            timed_wait(&b_full[sb], (bq / p.nb) & 1, st, 5);
             tc_fence_after();
             const uint32_t ha = smem_u32(hs + (size_t)sh * C::A_STAGE);
             const uint32_t wb = smem_u32(bs + (size_t)sb * C::B_STAGE);
@@ -253,7 +272,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
     uint32_t av = 0, rq = 0, hi_count = 0;                 // hi_count: chunks this half has produced
     for (int ray = pair; ray < nrays; ray += npairs, ++rq) {
       for (int v = 0; v < 2; ++v, ++av) {
-        mbar_wait(a1_full, av & 1);
+        timed_wait(a1_full, av & 1, st, 0);
         tc_fence_after();
         for (int cj = 0; cj < 9; ++cj, ++hi_count) {
           const int c = cj / 3, jj = cj - c * 3;
@@ -262,7 +281,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
           tmem_ld_wait();
           const uint32_t hq = hi_count * 2 + (uint32_t)half;                 // global H chunk index
           const int sh = hq % NH;
-          mbar_wait(&h_empty[sh], ((hq / NH) & 1) ^ 1);
+          timed_wait(&h_empty[sh], ((hq / NH) & 1) ^ 1, st, 1);
           uint8_t *dst = hs + (size_t)sh * C::A_STAGE;
           const int n0 = c * N1CH + half * (N1CH / 2) + jj * KS;
 #pragma unroll
@@ -288,7 +307,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
         if (lane == 0) mbar_arrive_cluster(a1_empty, 0);
       }
       // ---- acc3 -> V (fp32) and relu(key pre-activation) (bf16 hi/lo) ----
-      mbar_wait(a3_full, rq & 1);
+      timed_wait(a3_full, rq & 1, st, 2);
       tc_fence_after();
       const size_t grow = ((size_t)ray * 2 + rank) * ROWS + row;
       for (int e = 0; e < N3C; ++e) {
@@ -348,7 +367,9 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
     for (int ray = pair; ray < nrays; ray += npairs, ++it_ray) {
       const int scene = (p.g0 + ray) / p.R;
       const int buf = it_ray & 1;
-      asm volatile("bar.sync 1, 256;" ::: "memory");       // table[buf] complete; table[buf^1] no longer read
+      { long long tb0 = clock64();
+        asm volatile("bar.sync 1, 256;" ::: "memory");     // table[buf] complete; table[buf^1] no longer read
+        if (st) st[2] += (unsigned long long)(clock64() - tb0); }
       if (ray + npairs < nrays) build_taps(ray + npairs, buf ^ 1);
       const TapEntry *tb = taps + buf * (ROWS * 3 * 2);
       const float *th = tanhs + buf * (ROWS * 8);
@@ -358,7 +379,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
         const uint32_t xq = xq0 + (uint32_t)sidx;
         const int v = sidx >= K1_STAGES ? 1 : 0, kb = sidx - v * K1_STAGES;
         const int oc = (v == (int)rank) ? 0 : 1;           // own line (border taps) or cross-view taps
-        mbar_wait(&x_empty[gi], ((xq / NX) & 1) ^ 1);
+        timed_wait(&x_empty[gi], ((xq / NX) & 1) ^ 1, st, 0);
         uint8_t *dst = xs + (size_t)gi * C::A_STAGE;
         if (kb < K1_STAGES - 1) {
           const int ch0 = kb * KS;
@@ -462,6 +483,17 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
       }
     }
   }
+  if (st && lane == 0) {
+    const unsigned long long tot = (unsigned long long)(clock64() - t_begin);
+    int base = -1;
+    if (warp == 1) base = 0; else if (warp == 2) base = 8; else if (warp == 6) base = 12; else if (warp == 0) base = 16;
+    if (base >= 0) {
+      const int nfield = base == 0 ? 6 : (base == 8 ? 3 : (base == 12 ? 1 : 1));
+      for (int i = 0; i < nfield; ++i) atomicAdd(p.stats + base + i, st[i]);
+      atomicAdd(p.stats + base + nfield, tot);
+      if (base == 12) atomicAdd(p.stats + 14, st[2]);
+    }
+  }
   tc_fence_before();
   __syncthreads();
   cluster_sync();
@@ -472,6 +504,8 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
 }
 
 }  // namespace
+
+unsigned long long *g_fused_stats = nullptr;   // device buffer [32], set by car_debug_set_fused_stats
 
 // Launch for rays [g0,g1) of the current chunk.  Returns 0 or an error code.
 int launch_fused_encode(const car_render_args &a, int g0, int g1, const float *geom, float *value,
@@ -495,6 +529,7 @@ int launch_fused_encode(const car_render_args &a, int g0, int g1, const float *g
   p.H = a.H; p.W = a.W; p.R = a.R; p.g0 = g0; p.g1 = g1;
   p.geom = geom; p.bias1 = W1.bias; p.biasf = F.bias;
   p.value = value; p.kh_hi = kh_hi; p.kh_lo = kh_lo;
+  p.stats = g_fused_stats;
   const int a_stage = ROWS * KS * 2 * (split3 ? 2 : 1);
   const int b_stage = N1C * (N1CH / 2) * KS * 2 * (split3 ? 2 : 1);
   const size_t fixed = (size_t)(NX + NH) * a_stage + 2 * (ROWS * 3 * 2 * sizeof(TapEntry) + ROWS * 8 * 4) + (N1 + N3) * 4 +
@@ -527,3 +562,8 @@ int launch_fused_encode(const car_render_args &a, int g0, int g1, const float *g
 }
 
 }  // namespace car
+
+extern "C" int car_debug_set_fused_stats(void *dev_u64x32) {
+  car::g_fused_stats = reinterpret_cast<unsigned long long *>(dev_u64x32);
+  return 0;
+}

@@ -170,6 +170,10 @@ int car_gemm_umma_test(const uint16_t *a_hi, const uint16_t *a_lo, const uint16_
                        const uint16_t *w_lo, const float *bias, float *c, int M, int N, int K,
                        int split3, int relu, void *stream);
 
+/* Diagnostics: device buffer of 32 uint64 that the fused kernel fills with per-role barrier-wait
+ * cycle counts of pair 0 (layout documented in car_fused.cu); NULL disables. */
+int car_debug_set_fused_stats(void *dev_u64x32);
+
 /* CTA-pair (cta_group::2) tcgen05 GEMM, the building block of the fused per-ray kernel, exported
  * for tests: C[M][N] = A·W^T (+bias); N is processed as `nch` MMA chunks; `dump` (optional)
  * receives the raw TMEM image [pairs*2][128 lanes][N/2] of each pair's first tile. */

@@ -1,0 +1,28 @@
+"""Where does each role of the fused kernel wait?  (pair 0, leader CTA, cycles)"""
+import sys, os
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+import torch
+from cross_attention_renderer_b200 import synthetic, _lib
+from cross_attention_renderer_b200.models import CrossAttentionRenderer
+lib = _lib.load()
+prec = sys.argv[1] if len(sys.argv) > 1 else "fp32"
+b, H, P = 1, 256, 64
+inp = synthetic.to_device(synthetic.make_inputs(b, H, H, seed=1), "cuda")
+z = [t.cuda() for t in synthetic.make_features(b, H, seed=1)]
+m = CrossAttentionRenderer(n_view=2, npoints=P, precision=prec).cuda()
+m.load_state_dict(synthetic.make_state_dict(0), strict=False); m.H = m.W = H; m.pixel_val_to_cpu = False
+with torch.no_grad():
+    m(inp, z=z); torch.cuda.synchronize()
+    stats = torch.zeros(32, dtype=torch.int64, device="cuda")
+    lib.car_debug_set_fused_stats(stats.data_ptr())
+    m(inp, z=z); torch.cuda.synchronize()
+    lib.car_debug_set_fused_stats(None)
+s = stats.cpu().tolist()
+names = {0: "mma:a1_empty", 1: "mma:x_full", 2: "mma:b_full(g1)", 3: "mma:a3_empty", 4: "mma:h_full", 5: "mma:b_full(g3)", 6: "mma:TOTAL",
+         8: "epi:a1_full", 9: "epi:h_empty", 10: "epi:a3_full", 11: "epi:TOTAL", 12: "prod:x_empty", 13: "prod:TOTAL", 14: "prod:bar",
+         16: "tma:b_empty", 17: "tma:TOTAL"}
+rays_pair0 = (b * H * H + 73) // 74
+print(f"precision {prec}: pair-0 rays ~{rays_pair0}")
+for k, n in names.items():
+    tot = s[6] if k < 8 else s[11] if k < 12 else s[13] if k < 16 else s[17]
+    print(f"  {n:16s} {s[k]:14d} cyc  {100.0 * s[k] / max(1, tot):6.1f}%   {s[k] / rays_pair0:10.0f} cyc/ray")
