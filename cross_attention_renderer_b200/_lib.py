@@ -71,6 +71,7 @@ SYMBOLS = {
     "car_profile_begin": (C.c_int, []),
     "car_profile_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]),
     "car_debug_set_fused_stats": (C.c_int, [c_fp]),
+    "car_mma_rate_test": (C.c_int, [C.c_int] * 7 + [c_fp, c_fp]),
     "car_gemm_umma_test": (C.c_int, [c_fp] * 6 + [C.c_int] * 5 + [c_fp]),
     "car_gemm_pair_test": (C.c_int, [c_fp] * 7 + [C.c_int] * 8 + [c_fp]),
 }

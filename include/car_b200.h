@@ -174,6 +174,9 @@ int car_gemm_umma_test(const uint16_t *a_hi, const uint16_t *a_lo, const uint16_
  * cycle counts of pair 0 (layout documented in car_fused.cu); NULL disables. */
 int car_debug_set_fused_stats(void *dev_u64x32);
 
+/* Micro-benchmark: cycles for iters*nops back-to-back tcgen05.mma (M x N x 16, bf16) from resident smem. */
+int car_mma_rate_test(int cg, int M, int N, int sw, int iters, int nops, int ctas, void *out_u64, void *stream);
+
 /* CTA-pair (cta_group::2) tcgen05 GEMM, the building block of the fused per-ray kernel, exported
  * for tests: C[M][N] = A·W^T (+bias); N is processed as `nch` MMA chunks; `dump` (optional)
  * receives the raw TMEM image [pairs*2][128 lanes][N/2] of each pair's first tile. */
