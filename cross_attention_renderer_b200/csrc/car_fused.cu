@@ -203,7 +203,10 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
     }
   } else if (warp == 1) {
     // =========================== MMA issuer (leader CTA) ===========================
-    if (leader && lane == 0) {
+    // The whole warp stays converged; one elected lane issues.  Per stage the two operand
+    // descriptors are built once and advanced by compile-time constants inside fully unrolled
+    // loops, so the issue path is a handful of instructions per tcgen05.mma.
+    if (leader) {
       const uint32_t idesc1 = make_idesc_bf16(128, N1CH), idesc3 = make_idesc_bf16(128, N3CH);
       uint32_t bq = 0, xq = 0, hq = 0, av = 0, rq = 0;
       for (int ray = pair; ray < nrays; ray += npairs, ++rq) {
@@ -215,52 +218,62 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
             timed_wait(&x_full[sx], (xq / NX) & 1, st, 1);
             timed_wait(&b_full[sb], (bq / p.nb) & 1, st, 2);
             tc_fence_after();
-            const uint32_t xa = smem_u32(xs + (size_t)sx * C::A_STAGE);
-            const uint32_t wb = smem_u32(bs + (size_t)sb * C::B_STAGE);
-            const int ksteps = kb == K1_STAGES - 1 ? 1 : 2;
-            for (int k = 0; k < ksteps; ++k) {
-              const uint32_t koff = (uint32_t)k * 32;
-              const uint32_t acc = (kb | k) ? 1u : 0u;
-              for (int c = 0; c < N1C; ++c) {
-                const uint32_t d = tmem_base + ACC1_COL + (uint32_t)(c * (N1CH / 2));
-                const uint32_t w = wb + (uint32_t)(c * C::W1_CHUNK) + koff;
-                umma_f16<2>(d, make_desc<64>(xa + koff), make_desc<64>(w), idesc1, acc);
-                if (SPLIT == 3) {
-                  umma_f16<2>(d, make_desc<64>(xa + C::A_HALF + koff), make_desc<64>(w), idesc1, 1u);
-                  umma_f16<2>(d, make_desc<64>(xa + koff), make_desc<64>(w + C::B_HALF), idesc1, 1u);
+            if (elect_one()) {
+              const uint64_t da = make_desc<64>(smem_u32(xs + (size_t)sx * C::A_STAGE));
+              const uint64_t db = make_desc<64>(smem_u32(bs + (size_t)sb * C::B_STAGE));
+              const uint32_t d0 = tmem_base + ACC1_COL;
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                if (k == 1 && kb == K1_STAGES - 1) break;                   // last stage: 16 valid K columns
+                const uint32_t acc = (kb | k) ? 1u : 0u;
+#pragma unroll
+                for (int c = 0; c < N1C; ++c) {
+                  const uint64_t a = da + (uint64_t)((k * 32) >> 4);
+                  const uint64_t w = db + (uint64_t)((c * C::W1_CHUNK + k * 32) >> 4);
+                  umma_f16<2>(d0 + c * (N1CH / 2), a, w, idesc1, acc);
+                  if (SPLIT == 3) {
+                    umma_f16<2>(d0 + c * (N1CH / 2), a + (uint64_t)(C::A_HALF >> 4), w, idesc1, 1u);
+                    umma_f16<2>(d0 + c * (N1CH / 2), a, w + (uint64_t)(C::B_HALF >> 4), idesc1, 1u);
+                  }
                 }
               }
+              umma_commit_pair(&x_empty[sx], 0x3);
+              umma_commit_pair(&b_empty[sb], 0x3);
+              if (kb == K1_STAGES - 1) umma_commit_pair(a1_full, 0x3);
             }
-            umma_commit_pair(&x_empty[sx], 0x3);
-            umma_commit_pair(&b_empty[sb], 0x3);
+            __syncwarp();
           }
-          umma_commit_pair(a1_full, 0x3);
           if (v == 0) { timed_wait(a3_empty, (rq & 1) ^ 1, st, 3); tc_fence_after(); }
           for (int q = 0; q < K3_STAGES; ++q, ++bq, ++hq) {
             const int sb = bq % p.nb, sh = hq % NH;
             timed_wait(&h_full[sh], (hq / NH) & 1, st, 4);
             timed_wait(&b_full[sb], (bq / p.nb) & 1, st, 5);
             tc_fence_after();
-            const uint32_t ha = smem_u32(hs + (size_t)sh * C::A_STAGE);
-            const uint32_t wb = smem_u32(bs + (size_t)sb * C::B_STAGE);
-            for (int k = 0; k < 2; ++k) {
-              const uint32_t koff = (uint32_t)k * 32;
-              const uint32_t acc = (v | q | k) ? 1u : 0u;
-              for (int e = 0; e < N3C; ++e) {
-                const uint32_t d = tmem_base + ACC3_COL + (uint32_t)(e * (N3CH / 2));
-                const uint32_t w = wb + (uint32_t)(e * C::F_CHUNK) + koff;
-                umma_f16<2>(d, make_desc<64>(ha + koff), make_desc<64>(w), idesc3, acc);
-                if (SPLIT == 3) {
-                  umma_f16<2>(d, make_desc<64>(ha + C::A_HALF + koff), make_desc<64>(w), idesc3, 1u);
-                  umma_f16<2>(d, make_desc<64>(ha + koff), make_desc<64>(w + C::B_HALF), idesc3, 1u);
+            if (elect_one()) {
+              const uint64_t da = make_desc<64>(smem_u32(hs + (size_t)sh * C::A_STAGE));
+              const uint64_t db = make_desc<64>(smem_u32(bs + (size_t)sb * C::B_STAGE));
+              const uint32_t d0 = tmem_base + ACC3_COL;
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const uint32_t acc = (v | q | k) ? 1u : 0u;
+#pragma unroll
+                for (int e = 0; e < N3C; ++e) {
+                  const uint64_t a = da + (uint64_t)((k * 32) >> 4);
+                  const uint64_t w = db + (uint64_t)((e * C::F_CHUNK + k * 32) >> 4);
+                  umma_f16<2>(d0 + e * (N3CH / 2), a, w, idesc3, acc);
+                  if (SPLIT == 3) {
+                    umma_f16<2>(d0 + e * (N3CH / 2), a + (uint64_t)(C::A_HALF >> 4), w, idesc3, 1u);
+                    umma_f16<2>(d0 + e * (N3CH / 2), a, w + (uint64_t)(C::B_HALF >> 4), idesc3, 1u);
+                  }
                 }
               }
+              umma_commit_pair(&h_empty[sh], 0x3);
+              umma_commit_pair(&b_empty[sb], 0x3);
+              if (v == 1 && q == K3_STAGES - 1) umma_commit_pair(a3_full, 0x3);
             }
-            umma_commit_pair(&h_empty[sh], 0x3);
-            umma_commit_pair(&b_empty[sb], 0x3);
+            __syncwarp();
           }
         }
-        umma_commit_pair(a3_full, 0x3);
       }
     }
   } else if (warp < 6) {

@@ -13,12 +13,13 @@ k_mma_rate(int M, int N, int iters, int nops, unsigned long long *out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
+  __shared__ uint64_t wbar[4];
   __shared__ uint32_t slot;
   // operands: A tile at 0 (up to 128 rows x SW bytes = 16 KB), B tile at 32 KB (up to 256 rows)
   for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
-  if (warp == 0 && lane == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0 && lane == 0) { mbar_init(&bar, 1); for (int i = 0; i < 4; ++i) mbar_init(&wbar[i], 1); fence_barrier_init(); }
   if (warp == 1) tmem_alloc<CG>(&slot, 512);
   fence_async_smem();
   tc_fence_before();
@@ -26,6 +27,23 @@ k_mma_rate(int M, int N, int iters, int nops, unsigned long long *out) {
   if (CG == 2) cluster_sync();
   tc_fence_after();
   const uint32_t tmem = slot;
+  if (nops < 0) {
+    // multi-warp issue test: -nops warps each stream `iters` MMAs (N <= 128) into their own accumulator
+    const int nw = -nops;
+    if (warp < nw && lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(M, N);
+      const uint32_t sa = smem_u32(smem) + warp * 8192, sb = smem_u32(smem + 32 * 1024) + warp * 16384;
+      long long t0 = clock64();
+      for (int i = 0; i < iters; ++i) {
+        const uint32_t koff = (uint32_t)(i & (SW / 32 - 1)) * 32;
+        umma_f16<CG>(tmem + (uint32_t)(warp * 128), make_desc<SW>(sa + koff), make_desc<SW>(sb + koff), idesc, 1u);
+      }
+      if (CG == 2) umma_commit_pair(&wbar[warp], 0x1); else umma_commit(&wbar[warp]);
+      mbar_wait(&wbar[warp], 0);
+      long long t1 = clock64();
+      if (blockIdx.x == 0) out[warp] = (unsigned long long)(t1 - t0);
+    }
+  } else
   if (warp == 0 && lane == 0 && rank == 0) {
     const uint32_t idesc = make_idesc_bf16(M, N);
     const uint32_t sa = smem_u32(smem), sb = smem_u32(smem + 32 * 1024);
