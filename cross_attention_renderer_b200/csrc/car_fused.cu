@@ -34,7 +34,8 @@ using namespace ptx;
 
 constexpr int KS = 32;                 // K per stage (bf16 elements) = one 64-byte swizzle row
 constexpr int ROWS = 64;               // sample rows per CTA
-constexpr int NX = 4, NH = 4;          // X / H ring depth
+constexpr int NX = 8;                  // X ring depth: each of the 4 gather groups owns 2 slots
+constexpr int NHMAX = 4;               // H ring depth is Cfg::NH (2 for the hi+lo mode, 4 for bf16)
 constexpr int N1 = 576, N1CH = 192, N1C = 3;      // GEMM1: 3 MMA chunks of 192
 constexpr int N3 = 416, N3CH = 208, N3C = 2;      // GEMM3: 2 MMA chunks of 208
 constexpr int K1_STAGES = 19;          // ceil(592 / 32); the last stage holds 16 valid columns
@@ -80,6 +81,7 @@ template <int SPLIT> struct Cfg {
   static constexpr int F_CHUNK = (N3CH / 2) * KS * 2;              // 6656 B
   static constexpr int B_HALF = N1C * W1_CHUNK;                    // 18432 B (>= N3C*F_CHUNK = 13312)
   static constexpr int B_STAGE = B_HALF * OPS;
+  static constexpr int NH = SPLIT == 3 ? 2 : 4;
 };
 
 __device__ __forceinline__ float downgrade(float x) {
@@ -111,10 +113,18 @@ __device__ __forceinline__ TapEntry make_taps(float gx, float gy, int w, int h, 
   return t;
 }
 
+// (a, b) -> packed bf16x2 hi = rn(a, b) and, when WITH_LO, lo = rn(a - hi.a, b - hi.b)
+template <bool WITH_LO = true>
 __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
-  float ra, rb, d0, d1;
-  hi = pack_bf16x2(a, b, ra, rb);
-  lo = pack_bf16x2(ra, rb, d0, d1);
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<uint32_t *>(&h);
+  if (WITH_LO) {
+    const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+    __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
+    lo = *reinterpret_cast<uint32_t *>(&l);
+  } else {
+    lo = 0;
+  }
 }
 
 template <int SPLIT, typename FT>
@@ -126,6 +136,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *xs = smem;                                       // NX x A_STAGE
+  constexpr int NH = C::NH;
   uint8_t *hs = xs + NX * C::A_STAGE;                       // NH x A_STAGE
   uint8_t *bs = hs + NH * C::A_STAGE;                       // nb x B_STAGE
   TapEntry *taps = reinterpret_cast<TapEntry *>(bs + (size_t)p.nb * C::B_STAGE);   // [2 buffers][64][3][2]
@@ -134,8 +145,8 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
   float *sbiasf = sbias1 + N1;                                                     // [416]
   uint64_t *bars = reinterpret_cast<uint64_t *>(sbiasf + N3);
   uint64_t *x_full = bars, *x_empty = x_full + NX;
-  uint64_t *h_full = x_empty + NX, *h_empty = h_full + NH;
-  uint64_t *b_full = h_empty + NH, *b_empty = b_full + MAXB;
+  uint64_t *h_full = x_empty + NX, *h_empty = h_full + NHMAX;
+  uint64_t *b_full = h_empty + NHMAX, *b_empty = b_full + MAXB;
   uint64_t *a1_full = b_empty + MAXB, *a1_empty = a1_full + 1;
   uint64_t *a3_full = a1_empty + 1, *a3_empty = a3_full + 1;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a3_empty + 1);
@@ -287,34 +298,39 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
       for (int v = 0; v < 2; ++v, ++av) {
         timed_wait(a1_full, av & 1, st, 0);
         tc_fence_after();
-        for (int cj = 0; cj < 9; ++cj, ++hi_count) {
+        uint32_t r[2][32];
+        tmem_ld32(tlane + ACC1_COL, r[0]);                                    // chunk 0 in flight
+#pragma unroll
+        for (int cj = 0; cj < 9; ++cj) {
           const int c = cj / 3, jj = cj - c * 3;
-          uint32_t r[32];
-          tmem_ld32(tlane + ACC1_COL + (uint32_t)(c * (N1CH / 2) + jj * KS), r);
-          tmem_ld_wait();
-          const uint32_t hq = hi_count * 2 + (uint32_t)half;                 // global H chunk index
+          tmem_ld_wait();                                                      // r[cj & 1] has landed
+          if (cj + 1 < 9) {                                                    // next chunk overlaps this one's math
+            const int c2 = (cj + 1) / 3, j2 = (cj + 1) - c2 * 3;
+            tmem_ld32(tlane + ACC1_COL + (uint32_t)(c2 * (N1CH / 2) + j2 * KS), r[(cj + 1) & 1]);
+          }
+          const uint32_t hq = (hi_count + cj) * 2 + (uint32_t)half;            // global H chunk index
           const int sh = hq % NH;
+          const int n0 = c * N1CH + half * (N1CH / 2) + jj * KS;
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float a = fmaxf(__uint_as_float(r[cj & 1][2 * i]) + sbias1[n0 + 2 * i], 0.f);
+            float b = fmaxf(__uint_as_float(r[cj & 1][2 * i + 1]) + sbias1[n0 + 2 * i + 1], 0.f);
+            split2<SPLIT == 3>(a, b, hi[i], lo[i]);
+          }
           timed_wait(&h_empty[sh], ((hq / NH) & 1) ^ 1, st, 1);
           uint8_t *dst = hs + (size_t)sh * C::A_STAGE;
-          const int n0 = c * N1CH + half * (N1CH / 2) + jj * KS;
 #pragma unroll
           for (int c16 = 0; c16 < 4; ++c16) {
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int n = c16 * 8 + i * 2;
-              float a = fmaxf(__uint_as_float(r[n]) + sbias1[n0 + n], 0.f);
-              float b = fmaxf(__uint_as_float(r[n + 1]) + sbias1[n0 + n + 1], 0.f);
-              split2(a, b, hi[i], lo[i]);
-            }
             const uint32_t off = swz_offset<64>(row, c16);
-            *reinterpret_cast<uint4 *>(dst + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            if (SPLIT == 3) *reinterpret_cast<uint4 *>(dst + C::A_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4 *>(dst + off) = make_uint4(hi[4 * c16], hi[4 * c16 + 1], hi[4 * c16 + 2], hi[4 * c16 + 3]);
+            if (SPLIT == 3) *reinterpret_cast<uint4 *>(dst + C::A_HALF + off) = make_uint4(lo[4 * c16], lo[4 * c16 + 1], lo[4 * c16 + 2], lo[4 * c16 + 3]);
           }
           fence_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(&h_full[sh], 0);
         }
+        hi_count += 9;
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(a1_empty, 0);
@@ -339,7 +355,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
           } else {
             uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) split2(fmaxf(vv[2 * i], 0.f), fmaxf(vv[2 * i + 1], 0.f), hi[i], lo[i]);
+            for (int i = 0; i < 4; ++i) split2<SPLIT == 3>(fmaxf(vv[2 * i], 0.f), fmaxf(vv[2 * i + 1], 0.f), hi[i], lo[i]);
             const size_t o = grow * 128 + (n0 - CAR_C_LAT);
             *reinterpret_cast<uint4 *>(p.kh_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             if (SPLIT == 3) *reinterpret_cast<uint4 *>(p.kh_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -392,8 +408,9 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
         const uint32_t xq = xq0 + (uint32_t)sidx;
         const int v = sidx >= K1_STAGES ? 1 : 0, kb = sidx - v * K1_STAGES;
         const int oc = (v == (int)rank) ? 0 : 1;           // own line (border taps) or cross-view taps
-        timed_wait(&x_empty[gi], ((xq / NX) & 1) ^ 1, st, 0);
-        uint8_t *dst = xs + (size_t)gi * C::A_STAGE;
+        const int sx = (int)(xq % NX);                        // == gi or gi + 4
+        timed_wait(&x_empty[sx], ((xq / NX) & 1) ^ 1, st, 0);
+        uint8_t *dst = xs + (size_t)sx * C::A_STAGE;
         if (kb < K1_STAGES - 1) {
           const int ch0 = kb * KS;
           const int lvl = ch0 < 256 ? 0 : (ch0 < 512 ? 1 : 2);
@@ -429,8 +446,8 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
                   acc.z = fmaf(x[i][k].z, wt[i][k], acc.z); acc.w = fmaf(x[i][k].w, wt[i][k], acc.w);
                 }
                 uint32_t h0, l0, h1, l1;
-                split2(acc.x, acc.y, h0, l0);
-                split2(acc.z, acc.w, h1, l1);
+                split2<SPLIT == 3>(acc.x, acc.y, h0, l0);
+                split2<SPLIT == 3>(acc.z, acc.w, h1, l1);
                 const uint32_t off = swz_offset<64>(rr, grp >> 1) + (uint32_t)((grp & 1) * 8);
                 *reinterpret_cast<uint2 *>(dst + off) = make_uint2(h0, h1);
                 if (SPLIT == 3) *reinterpret_cast<uint2 *>(dst + C::A_HALF + off) = make_uint2(l0, l1);
@@ -468,7 +485,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
               }
               uint32_t hi[4], lo[4];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) split2(a8[2 * j], a8[2 * j + 1], hi[j], lo[j]);
+              for (int j = 0; j < 4; ++j) split2<SPLIT == 3>(a8[2 * j], a8[2 * j + 1], hi[j], lo[j]);
               const uint32_t off = swz_offset<64>(rr, grp);
               *reinterpret_cast<uint4 *>(dst + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               if (SPLIT == 3) *reinterpret_cast<uint4 *>(dst + C::A_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -482,8 +499,8 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
             uint32_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
             if (c16 == 0) {
               const float *T = th + rr * 8 + v * 4;
-              split2(T[0], T[1], hi[0], lo[0]);
-              split2(T[2], 0.f, hi[1], lo[1]);
+              split2<SPLIT == 3>(T[0], T[1], hi[0], lo[0]);
+              split2<SPLIT == 3>(T[2], 0.f, hi[1], lo[1]);
             }
             const uint32_t off = swz_offset<64>(rr, c16);
             *reinterpret_cast<uint4 *>(dst + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -492,7 +509,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
         }
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&x_full[gi], 0);
+        if (lane == 0) mbar_arrive_cluster(&x_full[sx], 0);
       }
     }
   }
@@ -545,8 +562,9 @@ int launch_fused_encode(const car_render_args &a, int g0, int g1, const float *g
   p.stats = g_fused_stats;
   const int a_stage = ROWS * KS * 2 * (split3 ? 2 : 1);
   const int b_stage = N1C * (N1CH / 2) * KS * 2 * (split3 ? 2 : 1);
-  const size_t fixed = (size_t)(NX + NH) * a_stage + 2 * (ROWS * 3 * 2 * sizeof(TapEntry) + ROWS * 8 * 4) + (N1 + N3) * 4 +
-                       (2 * NX + 2 * NH + 2 * MAXB + 4) * 8 + 16 + 512;
+  const int nh = split3 ? 2 : 4;
+  const size_t fixed = (size_t)(NX + nh) * a_stage + 2 * (ROWS * 3 * 2 * sizeof(TapEntry) + ROWS * 8 * 4) + (N1 + N3) * 4 +
+                       (2 * NX + 2 * NHMAX + 2 * MAXB + 4) * 8 + 16 + 512;
   int nb = (int)((227 * 1024 - fixed) / b_stage);
   if (nb > MAXB) nb = MAXB;
   if (nb < 2) { set_error("fused encode: not enough shared memory"); return -21; }
