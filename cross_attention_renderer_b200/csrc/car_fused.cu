@@ -34,8 +34,8 @@ using namespace ptx;
 
 constexpr int KS = 32;                 // K per stage (bf16 elements) = one 64-byte swizzle row
 constexpr int ROWS = 64;               // sample rows per CTA
-constexpr int NX = 8;                  // X ring depth: each of the 4 gather groups owns 2 slots
-constexpr int NHMAX = 4;               // H ring depth is Cfg::NH (2 for the hi+lo mode, 4 for bf16)
+constexpr int NXMAX = 8;               // X ring depth is Cfg::NX (6 for the hi+lo mode, 8 for bf16)
+constexpr int NHMAX = 4;               // H ring depth
 constexpr int N1 = 576, N1CH = 192, N1C = 3;      // GEMM1: 3 MMA chunks of 192
 constexpr int N3 = 416, N3CH = 208, N3C = 2;      // GEMM3: 2 MMA chunks of 208
 constexpr int K1_STAGES = 19;          // ceil(592 / 32); the last stage holds 16 valid columns
@@ -81,7 +81,8 @@ template <int SPLIT> struct Cfg {
   static constexpr int F_CHUNK = (N3CH / 2) * KS * 2;              // 6656 B
   static constexpr int B_HALF = N1C * W1_CHUNK;                    // 18432 B (>= N3C*F_CHUNK = 13312)
   static constexpr int B_STAGE = B_HALF * OPS;
-  static constexpr int NH = SPLIT == 3 ? 2 : 4;
+  static constexpr int NH = 4;
+  static constexpr int NX = SPLIT == 3 ? 6 : 8;
 };
 
 __device__ __forceinline__ float downgrade(float x) {
@@ -136,7 +137,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *xs = smem;                                       // NX x A_STAGE
-  constexpr int NH = C::NH;
+  constexpr int NH = C::NH, NX = C::NX;
   uint8_t *hs = xs + NX * C::A_STAGE;                       // NH x A_STAGE
   uint8_t *bs = hs + NH * C::A_STAGE;                       // nb x B_STAGE
   TapEntry *taps = reinterpret_cast<TapEntry *>(bs + (size_t)p.nb * C::B_STAGE);   // [2 buffers][64][3][2]
@@ -144,8 +145,8 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
   float *sbias1 = tanhs + 2 * ROWS * 8;                                                // [576]
   float *sbiasf = sbias1 + N1;                                                     // [416]
   uint64_t *bars = reinterpret_cast<uint64_t *>(sbiasf + N3);
-  uint64_t *x_full = bars, *x_empty = x_full + NX;
-  uint64_t *h_full = x_empty + NX, *h_empty = h_full + NHMAX;
+  uint64_t *x_full = bars, *x_empty = x_full + NXMAX;
+  uint64_t *h_full = x_empty + NXMAX, *h_empty = h_full + NHMAX;
   uint64_t *b_full = h_empty + NHMAX, *b_empty = b_full + MAXB;
   uint64_t *a1_full = b_empty + MAXB, *a1_empty = a1_full + 1;
   uint64_t *a3_full = a1_empty + 1, *a3_empty = a3_full + 1;
@@ -408,8 +409,8 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
         const uint32_t xq = xq0 + (uint32_t)sidx;
         const int v = sidx >= K1_STAGES ? 1 : 0, kb = sidx - v * K1_STAGES;
         const int oc = (v == (int)rank) ? 0 : 1;           // own line (border taps) or cross-view taps
-        const int sx = (int)(xq % NX);                        // == gi or gi + 4
-        timed_wait(&x_empty[sx], ((xq / NX) & 1) ^ 1, st, 0);
+        const int sx = (int)(xq % NX);
+        const uint32_t xpar = ((xq / NX) & 1) ^ 1;            // wait for the slot only right before the first store
         uint8_t *dst = xs + (size_t)sx * C::A_STAGE;
         if (kb < K1_STAGES - 1) {
           const int ch0 = kb * KS;
@@ -420,38 +421,39 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
           const int w = lvl == 0 ? p.W / 4 : (lvl == 1 ? p.W / 2 : p.W);
           const FT *img = fbase[lvl] + (size_t)(scene * 2 + v) * h * w * Cc + coff;
           if (sizeof(FT) == 4) {
-            // 64 rows x 8 groups of 4 channels = 512 items; thread handles items gt + 64*i
+            // 64 rows x 8 groups of 4 channels = 512 items; thread handles items gt + 64*i, i = 0..7,
+            // with a rolling window of 4 items (16 x LDG.128) in flight
+            float4 x[4][4];
+            float wt[4][4];
+            auto load_item = [&](int slot, int i) {
+              const int item = gt + 64 * i, rr = item >> 3, grp = item & 7;
+              const TapEntry t = tb[(rr * 3 + lvl) * 2 + oc];
 #pragma unroll
-            for (int round = 0; round < 2; ++round) {
-              float4 x[4][4];
-              float wt[4][4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int item = gt + 64 * (round * 4 + i), rr = item >> 3, grp = item & 7;
-                const TapEntry t = tb[(rr * 3 + lvl) * 2 + oc];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  wt[i][k] = t.off[k] >= 0 ? t.w[k] : 0.f;
-                  const int o = t.off[k] >= 0 ? t.off[k] : 0;
-                  x[i][k] = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(img) + (size_t)o * Cc + grp * 4));
-                }
+              for (int k = 0; k < 4; ++k) {
+                wt[slot][k] = t.off[k] >= 0 ? t.w[k] : 0.f;
+                const int o = t.off[k] >= 0 ? t.off[k] : 0;
+                x[slot][k] = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(img) + (size_t)o * Cc + grp * 4));
               }
+            };
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int item = gt + 64 * (round * 4 + i), rr = item >> 3, grp = item & 7;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < 4; ++i) load_item(i, i);
+            timed_wait(&x_empty[sx], xpar, st, 0);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  acc.x = fmaf(x[i][k].x, wt[i][k], acc.x); acc.y = fmaf(x[i][k].y, wt[i][k], acc.y);
-                  acc.z = fmaf(x[i][k].z, wt[i][k], acc.z); acc.w = fmaf(x[i][k].w, wt[i][k], acc.w);
-                }
-                uint32_t h0, l0, h1, l1;
-                split2<SPLIT == 3>(acc.x, acc.y, h0, l0);
-                split2<SPLIT == 3>(acc.z, acc.w, h1, l1);
-                const uint32_t off = swz_offset<64>(rr, grp >> 1) + (uint32_t)((grp & 1) * 8);
-                *reinterpret_cast<uint2 *>(dst + off) = make_uint2(h0, h1);
-                if (SPLIT == 3) *reinterpret_cast<uint2 *>(dst + C::A_HALF + off) = make_uint2(l0, l1);
+            for (int i = 0; i < 8; ++i) {
+              const int item = gt + 64 * i, rr = item >> 3, grp = item & 7, sl = i & 3;
+              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                acc.x = fmaf(x[sl][k].x, wt[sl][k], acc.x); acc.y = fmaf(x[sl][k].y, wt[sl][k], acc.y);
+                acc.z = fmaf(x[sl][k].z, wt[sl][k], acc.z); acc.w = fmaf(x[sl][k].w, wt[sl][k], acc.w);
               }
+              if (i + 4 < 8) load_item(sl, i + 4);
+              uint32_t h0, l0, h1, l1;
+              split2<SPLIT == 3>(acc.x, acc.y, h0, l0);
+              split2<SPLIT == 3>(acc.z, acc.w, h1, l1);
+              const uint32_t off = swz_offset<64>(rr, grp >> 1) + (uint32_t)((grp & 1) * 8);
+              *reinterpret_cast<uint2 *>(dst + off) = make_uint2(h0, h1);
+              if (SPLIT == 3) *reinterpret_cast<uint2 *>(dst + C::A_HALF + off) = make_uint2(l0, l1);
             }
           } else {
             // bf16 maps: 64 rows x 4 groups of 8 channels = 256 items; thread handles gt + 64*i
@@ -468,6 +470,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
                 x[i][k] = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint16_t *>(img) + (size_t)o * Cc + grp * 8));
               }
             }
+            timed_wait(&x_empty[sx], xpar, st, 0);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int item = gt + 64 * i, rr = item >> 2, grp = item & 3;
@@ -493,6 +496,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
           }
         } else {
           // last stage: [tanh(pt_v / 5) (3) | zeros]; only the first 16 K-columns are multiplied
+          timed_wait(&x_empty[sx], xpar, st, 0);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int item = gt + 64 * i, rr = item >> 2, c16 = item & 3;
@@ -562,9 +566,9 @@ int launch_fused_encode(const car_render_args &a, int g0, int g1, const float *g
   p.stats = g_fused_stats;
   const int a_stage = ROWS * KS * 2 * (split3 ? 2 : 1);
   const int b_stage = N1C * (N1CH / 2) * KS * 2 * (split3 ? 2 : 1);
-  const int nh = split3 ? 2 : 4;
-  const size_t fixed = (size_t)(NX + nh) * a_stage + 2 * (ROWS * 3 * 2 * sizeof(TapEntry) + ROWS * 8 * 4) + (N1 + N3) * 4 +
-                       (2 * NX + 2 * NHMAX + 2 * MAXB + 4) * 8 + 16 + 512;
+  const int nh = 4, nx = split3 ? 6 : 8;
+  const size_t fixed = (size_t)(nx + nh) * a_stage + 2 * (ROWS * 3 * 2 * sizeof(TapEntry) + ROWS * 8 * 4) + (N1 + N3) * 4 +
+                       (2 * NXMAX + 2 * NHMAX + 2 * MAXB + 4) * 8 + 16 + 512;
   int nb = (int)((227 * 1024 - fixed) / b_stage);
   if (nb > MAXB) nb = MAXB;
   if (nb < 2) { set_error("fused encode: not enough shared memory"); return -21; }
