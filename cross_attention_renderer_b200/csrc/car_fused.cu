@@ -309,6 +309,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
             const int c2 = (cj + 1) / 3, j2 = (cj + 1) - c2 * 3;
             tmem_ld32(tlane + ACC1_COL + (uint32_t)(c2 * (N1CH / 2) + j2 * KS), r[(cj + 1) & 1]);
           }
+          long long tc0 = st ? clock64() : 0;
           const uint32_t hq = (hi_count + cj) * 2 + (uint32_t)half;            // global H chunk index
           const int sh = hq % NH;
           const int n0 = c * N1CH + half * (N1CH / 2) + jj * KS;
@@ -319,7 +320,9 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
             float b = fmaxf(__uint_as_float(r[cj & 1][2 * i + 1]) + sbias1[n0 + 2 * i + 1], 0.f);
             split2<SPLIT == 3>(a, b, hi[i], lo[i]);
           }
+          if (st) st[3] += (unsigned long long)(clock64() - tc0);
           timed_wait(&h_empty[sh], ((hq / NH) & 1) ^ 1, st, 1);
+          tc0 = st ? clock64() : 0;
           uint8_t *dst = hs + (size_t)sh * C::A_STAGE;
 #pragma unroll
           for (int c16 = 0; c16 < 4; ++c16) {
@@ -327,9 +330,12 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
             *reinterpret_cast<uint4 *>(dst + off) = make_uint4(hi[4 * c16], hi[4 * c16 + 1], hi[4 * c16 + 2], hi[4 * c16 + 3]);
             if (SPLIT == 3) *reinterpret_cast<uint4 *>(dst + C::A_HALF + off) = make_uint4(lo[4 * c16], lo[4 * c16 + 1], lo[4 * c16 + 2], lo[4 * c16 + 3]);
           }
+          if (st) { st[3] += (unsigned long long)(clock64() - tc0); tc0 = clock64(); }
           fence_async_smem();
+          if (st) { st[4] += (unsigned long long)(clock64() - tc0); tc0 = clock64(); }
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(&h_full[sh], 0);
+          if (st) st[5] += (unsigned long long)(clock64() - tc0);
         }
         hi_count += 9;
         tc_fence_before();
@@ -339,30 +345,48 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
       // ---- acc3 -> V (fp32) and relu(key pre-activation) (bf16 hi/lo) ----
       timed_wait(a3_full, rq & 1, st, 2);
       tc_fence_after();
+      const long long td0 = st ? clock64() : 0;
       const size_t grow = ((size_t)ray * 2 + rank) * ROWS + row;
-      for (int e = 0; e < N3C; ++e) {
-        for (int j0 = 0; j0 < N3CH / 2; j0 += 8) {
-          uint32_t r[8];
-          tmem_ld8(tlane + ACC3_COL + (uint32_t)(e * (N3CH / 2) + j0), r);
-          tmem_ld_wait();
-          const int n0 = e * N3CH + half * (N3CH / 2) + j0;                 // 0..415, multiple of 8
+      // per lane: 104 accumulator columns per MMA chunk = 3 x 32 + 8; 32 fp32 = one 128-byte line
+      auto emit = [&](const uint32_t *r, int n0, int cnt) {                // cnt = 32 or 8 columns from n0
+#pragma unroll
+        for (int i0 = 0; i0 < 32; i0 += 8) {
+          if (i0 >= cnt) break;
+          const int n = n0 + i0;
           float vv[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) vv[i] = __uint_as_float(r[i]) + sbiasf[n0 + i];
-          if (n0 < CAR_C_LAT) {
-            float *o = p.value + grow * CAR_C_LAT + n0;
+          for (int i = 0; i < 8; ++i) vv[i] = __uint_as_float(r[i0 + i]) + sbiasf[n + i];
+          if (n < CAR_C_LAT) {
+            float *o = p.value + grow * CAR_C_LAT + n;
             *reinterpret_cast<float4 *>(o) = make_float4(vv[0], vv[1], vv[2], vv[3]);
             *reinterpret_cast<float4 *>(o + 4) = make_float4(vv[4], vv[5], vv[6], vv[7]);
           } else {
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) split2<SPLIT == 3>(fmaxf(vv[2 * i], 0.f), fmaxf(vv[2 * i + 1], 0.f), hi[i], lo[i]);
-            const size_t o = grow * 128 + (n0 - CAR_C_LAT);
+            const size_t o = grow * 128 + (n - CAR_C_LAT);
             *reinterpret_cast<uint4 *>(p.kh_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             if (SPLIT == 3) *reinterpret_cast<uint4 *>(p.kh_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
         }
+      };
+#pragma unroll
+      for (int e = 0; e < N3C; ++e) {
+        const uint32_t tcol = tlane + ACC3_COL + (uint32_t)(e * (N3CH / 2));
+        const int nb0 = e * N3CH + half * (N3CH / 2);
+        uint32_t ra[32], rb[32], rc[8];
+        tmem_ld32(tcol, ra);
+        tmem_ld32(tcol + 32, rb);
+        tmem_ld_wait();
+        emit(ra, nb0, 32);
+        tmem_ld32(tcol + 64, ra);
+        tmem_ld8(tcol + 96, rc);
+        emit(rb, nb0 + 32, 32);
+        tmem_ld_wait();
+        emit(ra, nb0 + 64, 32);
+        emit(rc, nb0 + 96, 8);
       }
+      if (st) st[6] += (unsigned long long)(clock64() - td0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(a3_empty, 0);
@@ -511,22 +535,20 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
             if (SPLIT == 3) *reinterpret_cast<uint4 *>(dst + C::A_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
         }
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&x_full[sx], 0);
+        { const long long tf0 = st ? clock64() : 0;
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&x_full[sx], 0);
+          if (st) st[3] += (unsigned long long)(clock64() - tf0); }
       }
     }
   }
   if (st && lane == 0) {
     const unsigned long long tot = (unsigned long long)(clock64() - t_begin);
-    int base = -1;
-    if (warp == 1) base = 0; else if (warp == 2) base = 8; else if (warp == 6) base = 12; else if (warp == 0) base = 16;
-    if (base >= 0) {
-      const int nfield = base == 0 ? 6 : (base == 8 ? 3 : (base == 12 ? 1 : 1));
-      for (int i = 0; i < nfield; ++i) atomicAdd(p.stats + base + i, st[i]);
-      atomicAdd(p.stats + base + nfield, tot);
-      if (base == 12) atomicAdd(p.stats + 14, st[2]);
-    }
+    if (warp == 1) { for (int i = 0; i < 6; ++i) atomicAdd(p.stats + i, st[i]); atomicAdd(p.stats + 6, tot); }
+    else if (warp == 2) { for (int i = 0; i < 7; ++i) atomicAdd(p.stats + 8 + i, st[i]); atomicAdd(p.stats + 15, tot); }
+    else if (warp == 6) { atomicAdd(p.stats + 16, st[0]); atomicAdd(p.stats + 17, tot); atomicAdd(p.stats + 18, st[2]); atomicAdd(p.stats + 19, st[3]); }
+    else if (warp == 0) { atomicAdd(p.stats + 20, st[0]); atomicAdd(p.stats + 21, tot); }
   }
   tc_fence_before();
   __syncthreads();

@@ -51,7 +51,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // arrive on the barrier at the same smem offset in CTA `rank` of the cluster
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t rank) {
   uint32_t a = mapa(smem_u32(bar), rank);
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(a) : "memory");
+  // default semantics (.release, .cta scope) as cutlass::arch::ClusterBarrier::arrive(cta_id): a
+  // cluster-scope release would make ptxas emit CCTL.IVALL (L1 invalidate, ~1.4k cycles measured)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(a) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
