@@ -60,6 +60,7 @@ struct Workspace {
   uint16_t *x_hi, *x_lo, *h1_hi, *h1_lo, *in_hi, *in_lo, *hid_hi, *hid_lo, *loc_hi, *loc_lo;
   // per ray
   float *zsum, *g, *rowbias, *zfin, *c18, *px, *pnet, *rgb3;
+  uint16_t *pr_hi, *pr_lo;     // per-ray bf16 operand copies for the tensor-core phi: [c18 32 | zfin 288 | relu(x) 128 | relu(net) 128]
   size_t bytes;
 };
 
@@ -105,6 +106,8 @@ Workspace carve(char *base, int precision, int P, int chunk) {
   w.px = (float *)take((size_t)chunk * 128 * 4);
   w.pnet = (float *)take((size_t)chunk * 128 * 4);
   w.rgb3 = (float *)take((size_t)chunk * 4 * 4);
+  w.pr_hi = (uint16_t *)take((size_t)chunk * 576 * 2);
+  w.pr_lo = (uint16_t *)take((size_t)chunk * 576 * 2);
   w.bytes = off;
   return w;
 }
@@ -158,6 +161,7 @@ void sample_stage_simt(const car_render_args &a, const Workspace &w, int g0, int
 
 // ---- per-sample stage, tcgen05 ------------------------------------------------------------
 int sample_stage_umma(const car_render_args &a, const Workspace &w, int g0, int g1, cudaStream_t st);
+int phi_stage_umma(const car_render_args &a, const Workspace &w, int g0, int g1, cudaStream_t st);
 
 // ---- per-ray colour MLP (resnet_block_fc.py:132-168), always exact fp32 ------------------
 void phi_stage(const car_render_args &a, const Workspace &w, int g0, int g1, cudaStream_t st) {
@@ -289,7 +293,8 @@ int car_render_forward(const car_render_args *pa) {
     dump(a.debug.q1, w.q1, row_off, rows, 128, st);
     dump(a.debug.q2, w.q2, row_off, rows, 128, st);
     dump(a.debug.zfinal, w.zfin, (size_t)(g0 - a.ray_begin), (size_t)(g1 - g0), CAR_C_LAT, st);
-    phi_stage(a, w, g0, g1, st);
+    if (a.precision == CAR_PREC_FP32_SIMT) phi_stage(a, w, g0, g1, st);
+    else { int rc = phi_stage_umma(a, w, g0, g1, st); if (rc) return rc; }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("kernel launch failed: %s", cudaGetErrorString(e)); return (int)e; }
   }
@@ -300,6 +305,39 @@ int car_render_forward(const car_render_args *pa) {
 
 namespace car {
 namespace {
+// Colour MLP phi on tcgen05 (M = rays): x is kept in fp32 (w.px); every layer's A operand is the
+// bf16 hi(+lo) copy emitted by the previous GEMM's epilogue (ReLU applied to the copy only).
+int phi_stage_umma(const car_render_args &a, const Workspace &w, int g0, int g1, cudaStream_t st) {
+  const car_weights &W = a.weights;
+  const int split3 = a.precision == CAR_PREC_FP32_3XBF16;
+  const int nr = g1 - g0;
+  StageScope sc(CAR_ST_PHI);
+  uint16_t *c_hi = w.pr_hi, *z_hi = c_hi + (size_t)nr * 32, *x_hi = z_hi + (size_t)nr * 288, *n_hi = x_hi + (size_t)nr * 128;
+  uint16_t *c_lo = w.pr_lo, *z_lo = c_lo + (size_t)nr * 32, *x_lo = z_lo + (size_t)nr * 288, *n_lo = x_lo + (size_t)nr * 128;
+  if (!split3) c_lo = z_lo = x_lo = n_lo = nullptr;
+  launch_phi_prep(a, g0, g1, w.c18, st);
+  launch_split_rows(w.c18, 32, c_hi, c_lo, nr, 32, st);
+  launch_split_rows(w.zfin, CAR_C_LAT, z_hi, z_lo, nr, CAR_C_LAT, st);
+  int rc;
+  auto mm = [&](const uint16_t *ah, const uint16_t *al, int lda, const car_mat &m, const GemmEpi &e, const UmmaOut &o) {
+    return launch_gemm_umma(ah, al, lda, m.hi, m.lo, m.K, nr, m.N, m.K, split3, e, o, st);
+  };
+  auto out = [&](float *f32, bool add, uint16_t *hi, uint16_t *lo) {
+    UmmaOut o; o.f32 = f32; o.f32_add = add ? f32 : nullptr; o.hi = hi; o.lo = lo; o.ldc = 128; return o; };
+  if ((rc = mm(c_hi, c_lo, 32, W.phi_in, epi(W.phi_in.bias, 0), out(w.px, false, nullptr, nullptr)))) return rc;
+  for (int i = 0; i < 3; ++i) {
+    // x += lin_z[i](z); operand copy = relu(x)
+    if ((rc = mm(z_hi, z_lo, CAR_C_LAT, W.phi_z[i], epi(W.phi_z[i].bias, 2, 0, 1), out(w.px, true, x_hi, x_lo)))) return rc;
+    // relu(fc_0(relu(x)))
+    if ((rc = mm(x_hi, x_lo, 128, W.phi_fc0[i], epi(W.phi_fc0[i].bias, 1), out(nullptr, false, n_hi, n_lo)))) return rc;
+    // x += fc_1(relu(net))
+    if ((rc = mm(n_hi, n_lo, 128, W.phi_fc1[i], epi(W.phi_fc1[i].bias, 0, 0, 1), out(w.px, true, nullptr, nullptr)))) return rc;
+  }
+  gemm(w.px, 128, W.phi_out, w.rgb3, 3, nr, epi(W.phi_out.bias, 0, 1, 0), st);       // N = 3: exact fp32
+  launch_finalize(a, g0, g1, w.rgb3, w.overlap, st);
+  return 0;
+}
+
 // Tensor-core per-sample stage: same dataflow as sample_stage_simt with every GEMM on
 // tcgen05 (car_gemm_umma.cu), operands kept as bf16 hi(+lo) between stages.
 int sample_stage_umma(const car_render_args &a, const Workspace &w, int g0, int g1, cudaStream_t st) {

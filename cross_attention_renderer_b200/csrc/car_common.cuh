@@ -61,7 +61,7 @@ struct GemmEpi {
   const float *row_bias;    // [M / rows_per_group][N] or null (per-ray bias)
   int rows_per_group;
   int relu_in;              // apply relu to A on load
-  int relu_out;
+  int relu_out;             // tcgen05 GEMM: 2 = ReLU only on the bf16 operand copy, fp32 output stays linear
   int accumulate;           // C += result
 };
 void launch_gemm_simt(const float *A, int lda, const float *W, int ldw, float *C, int ldc, int M,
@@ -80,6 +80,7 @@ void launch_finalize(const car_render_args &a, int g0, int g1, const float *rgb3
 // ---- car_gemm_umma.cu ------------------------------------------------------
 struct UmmaOut {
   float *f32;               // [M][ldc] fp32 output or null
+  const float *f32_add = nullptr;   // with GemmEpi::accumulate: fp32 [M][ldc] added to the product (may alias f32)
   uint16_t *hi, *lo;        // [M][ldc] bf16 split output or null
   int ldc;
 };

@@ -30,7 +30,8 @@ constexpr int MAX_STAGES = 8;
 struct UmmaParams {
   int M, N, K, BN, stages, tmem_cols;
   const float *bias, *row_bias;
-  int rows_per_group, relu;
+  int rows_per_group, relu;            // relu: 0 none, 1 on every output, 2 only on the bf16 operand copy
+  const float *add_src;                // optional fp32 [M][ldc] added before activation (may alias out_f32)
   float *out_f32;
   uint16_t *out_hi, *out_lo;
   int ldc;
@@ -239,43 +240,70 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
       const int row = m0 + sub * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * acc_stride);
       const float *rb = (p.row_bias && row < p.M) ? p.row_bias + (size_t)(row / p.rows_per_group) * p.N : nullptr;
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + (uint32_t)c0, r);
-        tmem_ld_wait();
-        if (row < p.M) {
-          float v[16];
+      // 32 accumulator columns per step: one 128-byte line of fp32 (or 64 B of bf16) per lane
+      auto emit = [&](const uint32_t *r, int c0, int cnt) {
+        if (row >= p.M) return;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float x = __uint_as_float(r[i]);
-            int n = n0 + c0 + i;
-            if (p.bias) x += __ldg(p.bias + n);
-            if (rb) x += __ldg(rb + n);
-            if (p.relu) x = fmaxf(x, 0.f);
+        for (int i0 = 0; i0 < 32; i0 += 8) {
+          if (i0 >= cnt) break;
+          const int n = n0 + c0 + i0;
+          const size_t o = (size_t)row * p.ldc + n;
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float x = __uint_as_float(r[i0 + i]);
+            if (p.bias) x += __ldg(p.bias + n + i);
+            if (rb) x += __ldg(rb + n + i);
             v[i] = x;
           }
-          size_t o = (size_t)row * p.ldc + n0 + c0;
-          if (p.out_f32) {
+          if (p.add_src) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(p.add_src + o);
+            const float4 a1 = *reinterpret_cast<const float4 *>(p.add_src + o + 4);
+            v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
+            v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+          }
+          if (p.relu == 1) {
 #pragma unroll
-            for (int i = 0; i < 16; i += 4)
-              *reinterpret_cast<float4 *>(p.out_f32 + o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (p.out_f32) {
+            *reinterpret_cast<float4 *>(p.out_f32 + o) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4 *>(p.out_f32 + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
           }
           if (p.out_hi) {
-            uint32_t hi[8], lo[8];
+            uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float ra, rbb;
-              hi[i] = pack_bf16x2(v[2 * i], v[2 * i + 1], ra, rbb);
-              float d0, d1;
+            for (int i = 0; i < 4; ++i) {
+              float x0 = v[2 * i], x1 = v[2 * i + 1];
+              if (p.relu == 2) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }   // ReLU only on the operand copy
+              float ra, rbb, d0, d1;
+              hi[i] = pack_bf16x2(x0, x1, ra, rbb);
               lo[i] = pack_bf16x2(ra, rbb, d0, d1);
             }
             *reinterpret_cast<uint4 *>(p.out_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4 *>(p.out_hi + o + 8) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-            if (p.out_lo) {
-              *reinterpret_cast<uint4 *>(p.out_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-              *reinterpret_cast<uint4 *>(p.out_lo + o + 8) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-            }
+            if (p.out_lo) *reinterpret_cast<uint4 *>(p.out_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
+        }
+      };
+      {
+        uint32_t r0[32], r1[32];
+        const int n32 = p.BN / 32;
+        if (n32 > 0) tmem_ld32(taddr, r0);
+        for (int j = 0; j < n32; j += 2) {
+          tmem_ld_wait();
+          if (j + 1 < n32) tmem_ld32(taddr + (uint32_t)((j + 1) * 32), r1);
+          emit(r0, j * 32, 32);
+          if (j + 1 < n32) {
+            tmem_ld_wait();
+            if (j + 2 < n32) tmem_ld32(taddr + (uint32_t)((j + 2) * 32), r0);
+            emit(r1, (j + 1) * 32, 32);
+          }
+        }
+        if (p.BN & 16) {
+          uint32_t rt[16];
+          tmem_ld16(taddr + (uint32_t)(n32 * 32), rt);
+          tmem_ld_wait();
+          emit(rt, n32 * 32, 16);
         }
       }
       tcgen05_fence_before();
@@ -362,6 +390,7 @@ int launch_gemm_umma(const uint16_t *a_hi, const uint16_t *a_lo, int lda, const 
   p.tmem_cols = BN <= 64 ? 128 : (BN <= 128 ? 256 : 512);
   p.bias = epi.bias; p.row_bias = epi.row_bias; p.rows_per_group = epi.rows_per_group > 0 ? epi.rows_per_group : 1;
   p.relu = epi.relu_out;
+  p.add_src = epi.accumulate ? out.f32_add : nullptr;
   p.out_f32 = out.f32; p.out_hi = out.hi; p.out_lo = out.lo; p.ldc = out.ldc;
   size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
   static int sms = 0;
