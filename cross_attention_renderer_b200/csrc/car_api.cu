@@ -353,11 +353,20 @@ int sample_stage_umma(const car_render_args &a, const Workspace &w, int g0, int 
                 const UmmaOut &o) {
     return launch_gemm_umma(ah, al, lda, m.hi, m.lo, m.K, M, m.N, m.K, split3, e, o, st);
   };
-  launch_split_rows(w.geom + G_LOCAL, CAR_GEOM_STRIDE, w.loc_hi, split3 ? w.loc_lo : nullptr, rows, 16, st);
-  const bool fused = a.use_fused && a.P == 64 && W.kv_fold.hi && !a.debug.interp;
+  const bool fused = (a.use_fused & 1) && a.P == 64 && W.kv_fold.hi && !a.debug.interp;
+  const bool tail = fused && (a.use_fused & 2) && !a.debug.key && !a.debug.q2;
+  if (!tail) launch_split_rows(w.geom + G_LOCAL, CAR_GEOM_STRIDE, w.loc_hi, split3 ? w.loc_lo : nullptr, rows, 16, st);
   if (fused) {
     // gather + enc1 + (enc2 ∘ [value; key1]) in one CTA-pair kernel: V and relu(key1) per sample
     if ((rc = launch_fused_encode(a, g0, g1, w.geom, w.value, w.hid_hi, split3 ? w.hid_lo : nullptr, st))) return rc;
+    if (tail) {
+      // per-ray tail: K, Q1, attention round 1 | per-ray 288->128->128 | Q2, attention round 2
+      if ((rc = launch_tail(a, 0, g0, g1, w.geom, w.value, w.hid_hi, w.hid_lo, w.q1, w.zsum, nullptr, nullptr, st))) return rc;
+      gemm(w.zsum, CAR_C_LAT, W.enc_lat, w.g, 128, nr, epi(W.enc_lat.bias, 0), st);
+      gemm(w.g, 128, W.rep1_g, w.rowbias, 128, nr, epi(W.rep1_g.bias, 0), st);
+      if ((rc = launch_tail(a, 1, g0, g1, w.geom, w.value, nullptr, nullptr, w.q1, w.zsum, w.rowbias, w.zfin, st))) return rc;
+      return 0;
+    }
   } else {
     launch_gather(a, g0, g1, w.geom, nullptr, w.x_hi, w.x_lo, st);
     // A.7 encoder MLP on both views of every sample: M = rows*2

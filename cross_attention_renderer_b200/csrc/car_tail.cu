@@ -1,0 +1,457 @@
+// Per-ray attention tail (P == 64): the small per-sample MLPs and both attention rounds in two
+// kernels instead of five GEMM launches + two attention launches with every [rows x 128] fp32
+// intermediate round-tripping through HBM.
+//
+//   phase A (reference models.py:491,529,532-545,573-594)
+//     K  = key_map_2(relu(key_map(.)))            A operand: relu(key_map) bf16 hi/lo from the fused kernel
+//     Q1 = query_embed_2(relu(query_embed(local)))
+//     s  = <K,Q1>/16, joint softmax over the ray's 128 samples -> at_wt, at_wt_max, z_sum = sum a*V,
+//     expected depth.  Q1 is also written out (fp32) for phase B.
+//   (between the phases: encode_latent and query_repeat_embed[:, :128] per ray, M = rays)
+//   phase B (models.py:552-565)
+//     Q2 = query_repeat_embed_2(relu(query_repeat_embed[:,128:](local) + u_ray))
+//     s2 = <Q2,Q1>/16, softmax, z = sum a2*V + 2*z_sum
+//
+// One CTA = one ray at a time (UMMA M = 128 = the ray's 2x64 samples), persistent over the chunk:
+//   warp 0  TMA: relu(key_map) tile and the weight K-blocks (ring)
+//   warp 1  MMA issuer (tcgen05 cta_group::1, N = 128), accumulators in TMEM
+//   warps 2-5: one thread per sample row: TMEM -> bias/ReLU -> bf16 hi/lo A operand of the next
+//           GEMM (smem, 128B swizzle), row dots, softmax (shuffles + named barrier), V sums.
+#include <math.h>
+
+#include "car_common.cuh"
+#include "car_umma.cuh"
+
+namespace car {
+int make_tmap_bf16(CUtensorMap *tm, const uint16_t *base, int rows, int K, int ld, int box_rows, int box_k);
+
+namespace {
+using namespace ptx;
+
+constexpr int THREADS = 192;
+constexpr int NBMAX = 3;
+
+struct TailParams {
+  car_render_args a;                  // sizes, geometry outputs (at_wt, at_wt_max, depth_ray), cams.qinv
+  int g0, g1;
+  const float *geom;                  // (rows,32)
+  const float *value;                 // (rows,288) fp32
+  float *q1;                          // (rows,128) fp32: written in phase A, read in phase B
+  float *zsum;                        // (rays,288)
+  const float *rowbias;               // (rays,128)  phase B
+  float *zfin;                        // (rays,288)  phase B
+  const float *bias_k2, *bias_q1, *bias_q2, *bias_r2;
+  int nb;
+};
+
+template <int SPLIT> struct TCfg {
+  static constexpr int OPS = SPLIT == 3 ? 2 : 1;
+  static constexpr int KB_BYTES = 128 * 128;                  // one K-block (64 bf16) of a 128-row tile
+  static constexpr int TILE_HALF = 2 * KB_BYTES;              // 128 x 128 bf16 (hi part)
+  static constexpr int TILE = TILE_HALF * OPS;
+  static constexpr int B_HALF = KB_BYTES;                     // 128 weight rows x 64 K
+  static constexpr int B_STAGE = B_HALF * OPS;
+};
+
+template <bool WITH_LO>
+__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<uint32_t *>(&h);
+  if (WITH_LO) {
+    const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+    __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
+    lo = *reinterpret_cast<uint32_t *>(&l);
+  } else {
+    lo = 0;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ void rows_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+
+// PHASE 0 = A, 1 = B
+template <int SPLIT, int PHASE>
+__global__ void __launch_bounds__(THREADS, 1)
+k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUtensorMap tm_kh_lo,
+       const __grid_constant__ CUtensorMap tm_w0_hi, const __grid_constant__ CUtensorMap tm_w0_lo,   // key2 (A only)
+       const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_constant__ CUtensorMap tm_w1_lo,   // K=16 layer
+       const __grid_constant__ CUtensorMap tm_w2_hi, const __grid_constant__ CUtensorMap tm_w2_lo,   // 128x128 layer
+       TailParams p) {
+  using C = TCfg<SPLIT>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *at0 = smem;                                        // relu(key_map) tile (phase A)
+  uint8_t *at1 = at0 + (PHASE == 0 ? C::TILE : 0);            // local (first 32 B of each row) then the hidden tile
+  uint8_t *bs = at1 + C::TILE;
+  float *arow = reinterpret_cast<float *>(bs + (size_t)p.nb * C::B_STAGE);   // [128] softmax weights
+  float *part = arow + 128;                                                    // [4][288] per-warp V sums
+  float *red = part + 4 * CAR_C_LAT;                                           // [32] scratch
+  uint64_t *bars = reinterpret_cast<uint64_t *>(red + 32);
+  uint64_t *kh_full = bars, *kh_empty = bars + 1, *loc_full = bars + 2, *hid_full = bars + 3;
+  uint64_t *t_full = bars + 4, *k_full = bars + 5, *done = bars + 6;
+  uint64_t *b_full = bars + 8, *b_empty = b_full + NBMAX;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(b_empty + NBMAX);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nrays = p.g1 - p.g0;
+  const int P = 64;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_w1_hi);
+    prefetch_tmap(&tm_w2_hi);
+    mbar_init(kh_full, 1); mbar_init(kh_empty, 1); mbar_init(loc_full, 4); mbar_init(hid_full, 4);
+    mbar_init(t_full, 1); mbar_init(k_full, 1); mbar_init(done, 4);
+    for (int s = 0; s < p.nb; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t ACCK = 0, ACCT = 128;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      uint32_t bq = 0, it = 0;
+      auto load_w = [&](const CUtensorMap *hi, const CUtensorMap *lo, int k0) {
+        const int s = bq % p.nb;
+        mbar_wait(&b_empty[s], ((bq / p.nb) & 1) ^ 1);
+        uint8_t *st = bs + (size_t)s * C::B_STAGE;
+        mbar_expect_tx(&b_full[s], (uint32_t)C::B_STAGE);
+        tma_load_2d(st, hi, &b_full[s], k0, 0);
+        if (SPLIT == 3) tma_load_2d(st + C::B_HALF, lo, &b_full[s], k0, 0);
+        ++bq;
+      };
+      for (int ray = blockIdx.x; ray < nrays; ray += gridDim.x, ++it) {
+        if (PHASE == 0) {
+          mbar_wait(kh_empty, (it & 1) ^ 1);
+          mbar_expect_tx(kh_full, (uint32_t)C::TILE);
+          const int r0 = ray * 128;
+          tma_load_2d(at0, &tm_kh_hi, kh_full, 0, r0);
+          tma_load_2d(at0 + C::KB_BYTES, &tm_kh_hi, kh_full, 64, r0);
+          if (SPLIT == 3) {
+            tma_load_2d(at0 + C::TILE_HALF, &tm_kh_lo, kh_full, 0, r0);
+            tma_load_2d(at0 + C::TILE_HALF + C::KB_BYTES, &tm_kh_lo, kh_full, 64, r0);
+          }
+          load_w(&tm_w0_hi, &tm_w0_lo, 0);
+          load_w(&tm_w0_hi, &tm_w0_lo, 64);
+        }
+        load_w(&tm_w1_hi, &tm_w1_lo, 0);                 // K = 16 layer: columns 16..63 are OOB zero fill
+        load_w(&tm_w2_hi, &tm_w2_lo, 0);
+        load_w(&tm_w2_hi, &tm_w2_lo, 64);
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    const uint32_t idesc = make_idesc_bf16(128, 128);
+    uint32_t bq = 0, it = 0, tq = 0;
+    // one 64-wide K-block: `ksteps` MMAs (x3 in the split mode) of A(base a) x B(stage) into d
+    auto gemm_kb = [&](uint32_t d, uint32_t a_addr, int ksteps, bool first) {
+      const int s = bq % p.nb;
+      mbar_wait(&b_full[s], (bq / p.nb) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t da = make_desc<128>(a_addr);
+        const uint64_t db = make_desc<128>(smem_u32(bs + (size_t)s * C::B_STAGE));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k >= ksteps) break;
+          const uint32_t acc = (first && k == 0) ? 0u : 1u;
+          const uint64_t a = da + (uint64_t)((k * 32) >> 4), w = db + (uint64_t)((k * 32) >> 4);
+          umma_f16<1>(d, a, w, idesc, acc);
+          if (SPLIT == 3) {
+            umma_f16<1>(d, a + (uint64_t)(C::TILE_HALF >> 4), w, idesc, 1u);
+            umma_f16<1>(d, a, w + (uint64_t)(C::B_HALF >> 4), idesc, 1u);
+          }
+        }
+        umma_commit(&b_empty[s]);
+      }
+      __syncwarp();
+      ++bq;
+    };
+    for (int ray = blockIdx.x; ray < nrays; ray += gridDim.x, ++it) {
+      mbar_wait(done, (it & 1) ^ 1);                     // row threads finished reading both accumulators
+      tc_fence_after();
+      if (PHASE == 0) {
+        mbar_wait(kh_full, it & 1);
+        tc_fence_after();
+        gemm_kb(tmem_base + ACCK, smem_u32(at0), 4, true);
+        gemm_kb(tmem_base + ACCK, smem_u32(at0 + C::KB_BYTES), 4, false);
+        if (elect_one()) { umma_commit(kh_empty); umma_commit(k_full); }
+        __syncwarp();
+      }
+      mbar_wait(loc_full, it & 1);
+      tc_fence_after();
+      gemm_kb(tmem_base + ACCT, smem_u32(at1), 1, true);                    // K = 16 layer
+      if (elect_one()) umma_commit(t_full);
+      __syncwarp();
+      ++tq;
+      mbar_wait(hid_full, it & 1);
+      tc_fence_after();
+      gemm_kb(tmem_base + ACCT, smem_u32(at1), 4, true);
+      gemm_kb(tmem_base + ACCT, smem_u32(at1 + C::KB_BYTES), 4, false);
+      if (elect_one()) umma_commit(t_full);
+      __syncwarp();
+      ++tq;
+    }
+  } else {
+    // =========================== row threads (warps 2..5) ===========================
+    const int sub = warp & 3;
+    const int row = sub * 32 + lane;                     // 0..127: ctx = row >> 6, sample k = row & 63
+    const uint32_t tlane = tmem_base + ((uint32_t)(sub * 32) << 16);
+    const int rt = row;                                  // thread id among the 128 row threads (for column loops)
+    uint32_t it = 0, tq = 0;
+    auto write_loc = [&](int ray_l) {
+      // local_coords (16 fp32) -> bf16 hi(+lo), first 32 bytes of this row of the at1 tile (K-block 0)
+      const float *L = p.geom + ((size_t)ray_l * 128 + row) * CAR_GEOM_STRIDE + G_LOCAL;
+      const float4 l0 = *reinterpret_cast<const float4 *>(L), l1 = *reinterpret_cast<const float4 *>(L + 4);
+      const float4 l2 = *reinterpret_cast<const float4 *>(L + 8), l3 = *reinterpret_cast<const float4 *>(L + 12);
+      uint32_t hi[8], lo[8];
+      split2<SPLIT == 3>(l0.x, l0.y, hi[0], lo[0]); split2<SPLIT == 3>(l0.z, l0.w, hi[1], lo[1]);
+      split2<SPLIT == 3>(l1.x, l1.y, hi[2], lo[2]); split2<SPLIT == 3>(l1.z, l1.w, hi[3], lo[3]);
+      split2<SPLIT == 3>(l2.x, l2.y, hi[4], lo[4]); split2<SPLIT == 3>(l2.z, l2.w, hi[5], lo[5]);
+      split2<SPLIT == 3>(l3.x, l3.y, hi[6], lo[6]); split2<SPLIT == 3>(l3.z, l3.w, hi[7], lo[7]);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const uint32_t off = swz_offset<128>(row, c);
+        *reinterpret_cast<uint4 *>(at1 + off) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+        if (SPLIT == 3) *reinterpret_cast<uint4 *>(at1 + C::TILE_HALF + off) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(loc_full);
+    };
+    if ((int)blockIdx.x < nrays) write_loc(blockIdx.x);
+    for (int ray = blockIdx.x; ray < nrays; ray += gridDim.x, ++it) {
+      const int g = p.g0 + ray, scene = g / p.a.R, rr = g - scene * p.a.R;
+      const size_t grow = (size_t)ray * 128 + row;
+      // ---- hidden layer: accT -> (+bias | +row bias) -> ReLU -> bf16 hi/lo -> at1 ----
+      mbar_wait(t_full, tq & 1); ++tq;
+      tc_fence_after();
+      {
+        const float *hb = PHASE == 0 ? p.bias_q1 : p.rowbias + (size_t)ray * 128;
+        uint32_t r[32];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          tmem_ld32(tlane + ACCT + (uint32_t)(j * 32), r);
+          tmem_ld_wait();
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float x0 = fmaxf(__uint_as_float(r[2 * i]) + __ldg(hb + j * 32 + 2 * i), 0.f);
+            const float x1 = fmaxf(__uint_as_float(r[2 * i + 1]) + __ldg(hb + j * 32 + 2 * i + 1), 0.f);
+            split2<SPLIT == 3>(x0, x1, hi[i], lo[i]);
+          }
+          uint8_t *dst = at1 + (j >> 1) * C::KB_BYTES;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t off = swz_offset<128>(row, (j & 1) * 4 + c);
+            *reinterpret_cast<uint4 *>(dst + off) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+            if (SPLIT == 3) *reinterpret_cast<uint4 *>(dst + C::TILE_HALF + off) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+          }
+        }
+        tc_fence_before();
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(hid_full);
+      }
+      // ---- scores: <K,Q1> (phase A) or <Q2,Q1> (phase B), each thread its own row ----
+      float sc = 0.f;
+      if (PHASE == 0) { mbar_wait(k_full, it & 1); }
+      mbar_wait(t_full, tq & 1); ++tq;
+      tc_fence_after();
+      {
+        float *q1row = p.q1 + grow * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t rt_[32], rk[32];
+          tmem_ld32(tlane + ACCT + (uint32_t)(j * 32), rt_);
+          if (PHASE == 0) tmem_ld32(tlane + ACCK + (uint32_t)(j * 32), rk);
+          tmem_ld_wait();
+          if (PHASE == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float q[4], k4[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                q[e] = __uint_as_float(rt_[i + e]) + __ldg(p.bias_q2 + j * 32 + i + e);
+                k4[e] = __uint_as_float(rk[i + e]) + __ldg(p.bias_k2 + j * 32 + i + e);
+                sc = fmaf(k4[e], q[e], sc);
+              }
+              *reinterpret_cast<float4 *>(q1row + j * 32 + i) = make_float4(q[0], q[1], q[2], q[3]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 q = *reinterpret_cast<const float4 *>(q1row + j * 32 + i);
+              const float qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float x = __uint_as_float(rt_[i + e]) + __ldg(p.bias_r2 + j * 32 + i + e);
+                sc = fmaf(x, qq[e], sc);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(done);                  // accumulators and at1 may be reused
+      if (ray + (int)gridDim.x < nrays) write_loc(ray + gridDim.x);   // next ray's K=16 operand (at1 is free: hidden GEMM retired)
+      sc = sc / 16.0f;
+      // ---- joint softmax over the 128 samples of the ray ----
+      float mx = warp_max(sc);
+      if (lane == 0) red[sub] = mx;
+      rows_sync();
+      mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+      const float e = expf(sc - mx);
+      float sm = warp_sum(e);
+      if (lane == 0) red[4 + sub] = sm;
+      rows_sync();
+      sm = (red[4] + red[5]) + (red[6] + red[7]);
+      const float aw = e / sm;
+      arow[row] = aw;
+      const int ctx = row >> 6, kk = row & 63;
+      if (PHASE == 0) {
+        p.a.at_wt[((size_t)(scene * 2 + ctx) * p.a.R + rr) * P + kk] = aw;
+        // per-context argmax (first maximum): warp-level then across the two warps of the context
+        float bv = aw; int bi = kk;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { red[8 + sub] = bv; reinterpret_cast<int *>(red)[12 + sub] = bi; }
+        // expected 3-D point (models.py:577-582)
+        const float *G = p.geom + grow * CAR_GEOM_STRIDE + G_PTC;
+        const float w0 = warp_sum(aw * G[0]), w1 = warp_sum(aw * G[1]), w2 = warp_sum(aw * G[2]);
+        if (lane == 0) { red[16 + sub * 3] = w0; red[17 + sub * 3] = w1; red[18 + sub * 3] = w2; }
+      }
+      rows_sync();                                       // arow[], red[] visible
+      if (PHASE == 0 && rt < 2) {
+        const int c = rt;                                // context c = rows [64c, 64c+64) = subs 2c, 2c+1
+        const float v0 = red[8 + 2 * c], v1 = red[8 + 2 * c + 1];
+        const int i0 = reinterpret_cast<int *>(red)[12 + 2 * c], i1 = reinterpret_cast<int *>(red)[12 + 2 * c + 1];
+        p.a.at_wt_max[(size_t)(scene * 2 + c) * p.a.R + rr] = (v1 > v0) ? i1 : i0;
+      }
+      if (PHASE == 0 && rt == 2) {
+        const float x = (red[16] + red[19]) + (red[22] + red[25]);
+        const float y = (red[17] + red[20]) + (red[23] + red[26]);
+        const float z = (red[18] + red[21]) + (red[24] + red[27]);
+        const float *qi = p.a.cams.qinv + (size_t)scene * 16;
+        const float zc = ((qi[8] * x + qi[9] * y) + qi[10] * z) + qi[11];
+        p.a.depth_ray[(size_t)scene * p.a.R + rr] = fminf(fmaxf(zc, 0.f), 10.f);
+      }
+      // ---- weighted V sums: warp `sub` covers its 32 rows, lanes cover float4 columns ----
+      {
+        const float *V = p.value + ((size_t)ray * 128 + sub * 32) * CAR_C_LAT;
+        float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0, acc2 = acc0;
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+          const float a = arow[sub * 32 + i];
+          const float4 *vr = reinterpret_cast<const float4 *>(V + (size_t)i * CAR_C_LAT);
+          const float4 v0 = __ldg(vr + lane), v1 = __ldg(vr + 32 + lane);
+          acc0.x = fmaf(a, v0.x, acc0.x); acc0.y = fmaf(a, v0.y, acc0.y); acc0.z = fmaf(a, v0.z, acc0.z); acc0.w = fmaf(a, v0.w, acc0.w);
+          acc1.x = fmaf(a, v1.x, acc1.x); acc1.y = fmaf(a, v1.y, acc1.y); acc1.z = fmaf(a, v1.z, acc1.z); acc1.w = fmaf(a, v1.w, acc1.w);
+          if (lane < 8) {
+            const float4 v2 = __ldg(vr + 64 + lane);
+            acc2.x = fmaf(a, v2.x, acc2.x); acc2.y = fmaf(a, v2.y, acc2.y); acc2.z = fmaf(a, v2.z, acc2.z); acc2.w = fmaf(a, v2.w, acc2.w);
+          }
+        }
+        float4 *pp = reinterpret_cast<float4 *>(part + sub * CAR_C_LAT);
+        pp[lane] = acc0; pp[32 + lane] = acc1;
+        if (lane < 8) pp[64 + lane] = acc2;
+      }
+      rows_sync();
+      for (int c = rt; c < CAR_C_LAT; c += 128) {
+        const float z0 = part[0 * CAR_C_LAT + c] + part[1 * CAR_C_LAT + c];      // context 0 = rows 0..63
+        const float z1 = part[2 * CAR_C_LAT + c] + part[3 * CAR_C_LAT + c];      // context 1
+        if (PHASE == 0) {
+          p.zsum[(size_t)ray * CAR_C_LAT + c] = z0 + z1;                         // models.py:537-540
+        } else {
+          const float zs = p.zsum[(size_t)ray * CAR_C_LAT + c];
+          p.zfin[(size_t)ray * CAR_C_LAT + c] = (z0 + zs) + (z1 + zs);           // models.py:561-564
+        }
+      }
+      rows_sync();                                       // part[], arow[], red[] reused by the next ray
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 256);
+  }
+}
+
+}  // namespace
+
+// phase 0: needs kh (relu(key_map) hi/lo), writes q1, zsum, at_wt, at_wt_max, depth_ray
+// phase 1: needs rowbias, q1, zsum; writes zfin
+int launch_tail(const car_render_args &a, int phase, int g0, int g1, const float *geom, const float *value,
+                const uint16_t *kh_hi, const uint16_t *kh_lo, float *q1, float *zsum, const float *rowbias,
+                float *zfin, cudaStream_t st) {
+  const int split3 = a.precision == CAR_PREC_FP32_3XBF16;
+  const car_weights &W = a.weights;
+  if (a.P != 64) { set_error("tail kernel needs P == 64"); return -30; }
+  const int nrays = g1 - g0;
+  const car_mat &w0 = W.key2, &w1 = phase == 0 ? W.qry1 : W.rep1_loc, &w2 = phase == 0 ? W.qry2 : W.rep2;
+  CUtensorMap tk_h, tk_l, t0h, t0l, t1h, t1l, t2h, t2l;
+  int rc;
+  auto mk = [&](CUtensorMap *th, CUtensorMap *tl, const uint16_t *hi, const uint16_t *lo, int rows, int K) {
+    if ((rc = make_tmap_bf16(th, hi, rows, K, K, 128, 64))) return rc;
+    if (split3) { if ((rc = make_tmap_bf16(tl, lo, rows, K, K, 128, 64))) return rc; } else *tl = *th;
+    return 0;
+  };
+  if (phase == 0) { if (mk(&tk_h, &tk_l, kh_hi, kh_lo, nrays * 128, 128)) return rc; }
+  if (mk(&t0h, &t0l, w0.hi, w0.lo, 128, 128)) return rc;
+  if (mk(&t1h, &t1l, w1.hi, w1.lo, 128, 16)) return rc;
+  if (mk(&t2h, &t2l, w2.hi, w2.lo, 128, 128)) return rc;
+  if (phase != 0) { tk_h = t0h; tk_l = t0l; }
+  TailParams p;
+  p.a = a; p.g0 = g0; p.g1 = g1; p.geom = geom; p.value = value; p.q1 = q1; p.zsum = zsum;
+  p.rowbias = rowbias; p.zfin = zfin;
+  p.bias_k2 = W.key2.bias; p.bias_q1 = W.qry1.bias; p.bias_q2 = W.qry2.bias; p.bias_r2 = W.rep2.bias;
+  const int ops = split3 ? 2 : 1;
+  const size_t tile = 2 * 128 * 128 * ops, bstage = 128 * 128 * ops;
+  const size_t fixed = (phase == 0 ? 2 : 1) * tile + (128 + 4 * CAR_C_LAT + 32) * 4 + (8 + 2 * NBMAX) * 8 + 16 + 512;
+  int nb = (int)((227 * 1024 - fixed) / bstage);
+  if (nb > NBMAX) nb = NBMAX;
+  if (nb < 2) { set_error("tail: not enough shared memory"); return -31; }
+  p.nb = nb;
+  const size_t smem = fixed + (size_t)nb * bstage;
+  static int sms = 0;
+  if (!sms) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int grid = nrays < sms ? nrays : sms;
+  cudaError_t e = cudaSuccess;
+  prof_pre(CAR_ST_ATTENTION, st);
+#define CAR_TAIL(S, PH)                                                                              \
+  do {                                                                                               \
+    e = cudaFuncSetAttribute(k_tail<S, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+    if (e == cudaSuccess)                                                                            \
+      k_tail<S, PH><<<grid, THREADS, smem, st>>>(tk_h, tk_l, t0h, t0l, t1h, t1l, t2h, t2l, p);        \
+  } while (0)
+  if (split3) { if (phase == 0) CAR_TAIL(3, 0); else CAR_TAIL(3, 1); }
+  else { if (phase == 0) CAR_TAIL(1, 0); else CAR_TAIL(1, 1); }
+#undef CAR_TAIL
+  prof_post(st);
+  if (e != cudaSuccess) { set_error("tail: %s", cudaGetErrorString(e)); return (int)e; }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("tail launch: %s", cudaGetErrorString(e)); return (int)e; }
+  count_launch();
+  return 0;
+}
+
+}  // namespace car

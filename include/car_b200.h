@@ -143,7 +143,8 @@ typedef struct car_render_args {
   size_t workspace_bytes;
   car_debug debug;                /* all-NULL in production                                  */
   void *stream;                   /* cudaStream_t                                            */
-  int32_t use_fused;              /* 1: fused gather+encode kernel when eligible (P == 64)   */
+  int32_t use_fused;              /* bit 0: fused gather+encode kernel, bit 1: fused per-ray
+                                     attention tail (both need P == 64; else the unfused path) */
 } car_render_args;
 
 /* Rays are processed in chunks of `chunk_rays`; workspace scales with the chunk. */

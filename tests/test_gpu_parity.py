@@ -324,3 +324,40 @@ def test_fused_encode_matches_unfused(precision, feat):
         assert rel_err(cpu(outs[True]["rgb"]), ref["rgb"]) < 1e-4
         assert torch.allclose(cpu(taps[True]["value"]), _rows(ref["_I"]["value"], b, P), rtol=2e-4,
                               atol=2e-4 * float(ref["_I"]["value"].abs().max()))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fused_tail_matches(precision):
+    """Per-ray tail kernels (K/Q1/Q2 MLPs + both attention rounds) against the separate GEMM +
+    attention kernels, and against the oracle for the fp32 precision."""
+    b, H, Ht, P = 2, 64, 24, 64
+    inp = synthetic.make_inputs(b, H, Ht, seed=44, mode="mixed")
+    z = synthetic.make_features(b, H, seed=44)
+    sd = synthetic.make_state_dict(seed=44, peaky=True)
+    cams = orc.prepare_cameras(inp)
+    interval = torch.linspace(0, 1, P)
+    outs, taps = {}, {}
+    for mode in (1, 3):
+        model = make_model(sd, P, H, precision=precision, use_fused=mode)
+        taps[mode] = {"_keys": ("value", "q1", "zfinal")}
+        outs[mode] = run_cuda(model, inp, z, cams=cams, interval=interval, debug_taps=taps[mode])
+    tol = 2e-4 if precision == "fp32" else 3e-2
+    for k in ("q1", "zfinal"):
+        a, r = cpu(taps[3][k]), cpu(taps[1][k])
+        assert torch.isfinite(a).all(), k
+        assert float((a - r).abs().max() / r.abs().max()) < tol, k
+    o3, o1 = outs[3], outs[1]
+    assert rel_err(cpu(o3["rgb"]), cpu(o1["rgb"])) < (2e-4 if precision == "fp32" else 5e-2)
+    assert torch.allclose(cpu(o3["at_wt"]), cpu(o1["at_wt"]), rtol=5e-3 if precision == "fp32" else 0.2, atol=1e-5)
+    assert torch.equal(cpu(o3["valid_mask"]), cpu(o1["valid_mask"]))
+    if precision == "fp32":
+        with torch.no_grad():
+            ref = orc.render(sd, inp, z, H, H, P, interval=interval, cams=cams)
+        assert rel_err(cpu(o3["rgb"]), ref["rgb"]) < 1e-4
+        assert torch.allclose(cpu(o3["at_wt"]), ref["at_wt"], rtol=2e-3, atol=1e-6)
+        ok, worst = depth_close(cpu(o3["depth_ray"]), ref["depth_ray"], cpu(o3["at_wt"]), ref["at_wt"], b)
+        assert ok, worst
+        aw = ref["at_wt"]
+        top2 = aw.topk(2, dim=-1).values
+        decided = (top2[..., 0] - top2[..., 1]) > 1e-4 * top2[..., 0]
+        assert torch.equal(cpu(o3["at_wt_max"])[..., 0][decided], ref["at_wt_max"][..., 0][decided])
