@@ -232,15 +232,12 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
       __syncwarp();
       if (lane == 0) mbar_arrive(loc_full);
     };
-    if ((int)blockIdx.x < nrays) write_loc(blockIdx.x);
-    for (int ray = blockIdx.x; ray < nrays; ray += gridDim.x, ++it) {
-      const int g = p.g0 + ray, scene = g / p.a.R, rr = g - scene * p.a.R;
-      const size_t grow = (size_t)ray * 128 + row;
-      // ---- hidden layer: accT -> (+bias | +row bias) -> ReLU -> bf16 hi/lo -> at1 ----
+    // hidden layer: accT -> (+bias | +row bias) -> ReLU -> bf16 hi/lo -> at1 (A operand of the 128x128 layer)
+    auto drain_hidden = [&](int ray_l) {
       mbar_wait(t_full, tq & 1); ++tq;
       tc_fence_after();
       {
-        const float *hb = PHASE == 0 ? p.bias_q1 : p.rowbias + (size_t)ray * 128;
+        const float *hb = PHASE == 0 ? p.bias_q1 : p.rowbias + (size_t)ray_l * 128;
         uint32_t r[32];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -266,6 +263,11 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
         __syncwarp();
         if (lane == 0) mbar_arrive(hid_full);
       }
+    };
+    if ((int)blockIdx.x < nrays) { write_loc(blockIdx.x); drain_hidden(blockIdx.x); }
+    for (int ray = blockIdx.x; ray < nrays; ray += gridDim.x, ++it) {
+      const int g = p.g0 + ray, scene = g / p.a.R, rr = g - scene * p.a.R;
+      const size_t grow = (size_t)ray * 128 + row;
       // ---- scores: <K,Q1> (phase A) or <Q2,Q1> (phase B), each thread its own row ----
       float sc = 0.f;
       if (PHASE == 0) { mbar_wait(k_full, it & 1); }
@@ -354,11 +356,13 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
         const float zc = ((qi[8] * x + qi[9] * y) + qi[10] * z) + qi[11];
         p.a.depth_ray[(size_t)scene * p.a.R + rr] = fminf(fmaxf(zc, 0.f), 10.f);
       }
+      // next ray's hidden layer first: its 128x128 GEMM then runs while this ray's V sums are formed
+      if (ray + (int)gridDim.x < nrays) drain_hidden(ray + gridDim.x);
       // ---- weighted V sums: warp `sub` covers its 32 rows, lanes cover float4 columns ----
       {
         const float *V = p.value + ((size_t)ray * 128 + sub * 32) * CAR_C_LAT;
         float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0, acc2 = acc0;
-#pragma unroll 4
+#pragma unroll 8
         for (int i = 0; i < 32; ++i) {
           const float a = arow[sub * 32 + i];
           const float4 *vr = reinterpret_cast<const float4 *>(V + (size_t)i * CAR_C_LAT);
