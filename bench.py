@@ -301,7 +301,32 @@ def main():
                              "kernel": "k_gemm_simt (fp32 FFMA)" if args.precision == "fp32_simt" else "k_gemm_umma",
                              "avg_launch_ms": stage_ms["gemm_enc1"] / max(1, stage_ln["gemm_enc1"]),
                              "peak_source": peaks["source"] + " bf16 dense, sustained"}
-    roofline = roof.get(dom) or roof.get("gemm_enc1") or roof.get("gather")
+    if stage_ms.get("fused", 0) > 0:
+        # k_fused_encode: gather + encoder GEMMs of one ray chunk per launch.  Algorithmic bytes =
+        # bilinear tap bytes (n*P*2 gathers*576 ch*4 taps*elt per ray); algorithmic
+        # flops = 2*128*(592*576 + 576*416)*2 per ray (the 3xbf16 split executes 3x that).
+        t = stage_ms["fused"] * 1e-3
+        ach = rays_prof * tap_bytes / t / 1e9
+        flop_ray = 2 * 128 * (592 * 576 + 576 * 416) * 2 * (P / 64.0)
+        mma_mult = 3 if args.precision == "fp32" else 1
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", f"r01_ncu_fused_encode_{args.precision}.json")
+        if os.path.exists(prof):
+            try:
+                pj = json.load(open(prof))
+                traffic = (float(pj["dram__bytes_read.sum"].split()[0]) + float(pj["dram__bytes_write.sum"].split()[0])) * 1e6
+            except Exception:
+                traffic = None
+        roof["fused"] = {
+            "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+            "traffic": traffic, "kernel": "k_fused_encode", "avg_launch_ms": stage_ms["fused"] / max(1, stage_ln["fused"]),
+            "algorithmic_bytes_per_ray": tap_bytes, "peak_source": peaks["source"],
+            "note": "taps are served by L1/L2 (feature maps of a scene fit the 126 MB L2), hence DRAM traffic << tap bytes",
+            "tensor": {"algorithmic_tflops": rays_prof * flop_ray / t / 1e12,
+                       "mma_tflops_executed": rays_prof * flop_ray * mma_mult / t / 1e12,
+                       "peak_bf16_tflops_sustained": peaks["bf16_tflops_sustained"],
+                       "frac_executed": rays_prof * flop_ray * mma_mult / t / 1e12 / peaks["bf16_tflops_sustained"]}}
+    roofline = roof.get(dom) or roof.get("fused") or roof.get("gemm_enc1") or roof.get("gather")
     share = {k: round(v / max(1e-9, sum(stage_ms.values())), 4) for k, v in stage_ms.items() if v > 0}
 
     cpu_base = None

@@ -23,6 +23,7 @@
 #include "car_umma.cuh"
 
 namespace car {
+extern unsigned long long *g_fused_stats;
 int make_tmap_bf16(CUtensorMap *tm, const uint16_t *base, int rows, int K, int ld, int box_rows, int box_k);
 
 namespace {
@@ -42,6 +43,7 @@ struct TailParams {
   float *zfin;                        // (rays,288)  phase B
   const float *bias_k2, *bias_q1, *bias_q2, *bias_r2;
   int nb;
+  unsigned long long *stats;         // optional [16]: row-thread cycle accounting of CTA 0 (see scripts/tail_stalls.py)
 };
 
 template <int SPLIT> struct TCfg {
@@ -134,6 +136,20 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
         ++bq;
       };
       for (int ray = blockIdx.x; ray < nrays; ray += gridDim.x, ++it) {
+        {
+          // pull the next ray's V rows (and Q1 rows in phase B) into L2 ahead of the row threads
+          const int nx = ray + (it == 0 ? 0 : (int)gridDim.x);
+          for (int rr_ = nx; rr_ <= ray + (int)gridDim.x && rr_ < nrays; rr_ += gridDim.x) {
+            const char *vp = reinterpret_cast<const char *>(p.value + (size_t)rr_ * 128 * CAR_C_LAT);
+            for (int o = 0; o < 128 * CAR_C_LAT * 4; o += 16384)
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(vp + o), "r"(16384) : "memory");
+            if (PHASE == 1) {
+              const char *qp = reinterpret_cast<const char *>(p.q1 + (size_t)rr_ * 128 * 128);
+              for (int o = 0; o < 128 * 128 * 4; o += 16384)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(qp + o), "r"(16384) : "memory");
+            }
+          }
+        }
         if (PHASE == 0) {
           mbar_wait(kh_empty, (it & 1) ^ 1);
           mbar_expect_tx(kh_full, (uint32_t)C::TILE);
@@ -212,6 +228,9 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
     const uint32_t tlane = tmem_base + ((uint32_t)(sub * 32) << 16);
     const int rt = row;                                  // thread id among the 128 row threads (for column loops)
     uint32_t it = 0, tq = 0;
+    unsigned long long tacc[6] = {0, 0, 0, 0, 0, 0};     // 0 drain 1 score-wait 2 score 3 softmax 4 vsum 5 total
+    const bool rec = p.stats && blockIdx.x == 0 && warp == 2;
+    const long long tbeg = clock64();
     auto write_loc = [&](int ray_l) {
       // local_coords (16 fp32) -> bf16 hi(+lo), first 32 bytes of this row of the at1 tile (K-block 0)
       const float *L = p.geom + ((size_t)ray_l * 128 + row) * CAR_GEOM_STRIDE + G_LOCAL;
@@ -234,6 +253,7 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
     };
     // hidden layer: accT -> (+bias | +row bias) -> ReLU -> bf16 hi/lo -> at1 (A operand of the 128x128 layer)
     auto drain_hidden = [&](int ray_l) {
+      const long long td = clock64();
       mbar_wait(t_full, tq & 1); ++tq;
       tc_fence_after();
       {
@@ -263,6 +283,7 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
         __syncwarp();
         if (lane == 0) mbar_arrive(hid_full);
       }
+      tacc[0] += (unsigned long long)(clock64() - td);
     };
     if ((int)blockIdx.x < nrays) { write_loc(blockIdx.x); drain_hidden(blockIdx.x); }
     for (int ray = blockIdx.x; ray < nrays; ray += gridDim.x, ++it) {
@@ -270,9 +291,11 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
       const size_t grow = (size_t)ray * 128 + row;
       // ---- scores: <K,Q1> (phase A) or <Q2,Q1> (phase B), each thread its own row ----
       float sc = 0.f;
+      long long tt = clock64();
       if (PHASE == 0) { mbar_wait(k_full, it & 1); }
       mbar_wait(t_full, tq & 1); ++tq;
       tc_fence_after();
+      tacc[1] += (unsigned long long)(clock64() - tt); tt = clock64();
       {
         float *q1row = p.q1 + grow * 128;
 #pragma unroll
@@ -311,6 +334,7 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
       __syncwarp();
       if (lane == 0) mbar_arrive(done);                  // accumulators and at1 may be reused
       if (ray + (int)gridDim.x < nrays) write_loc(ray + gridDim.x);   // next ray's K=16 operand (at1 is free: hidden GEMM retired)
+      tacc[2] += (unsigned long long)(clock64() - tt); tt = clock64();
       sc = sc / 16.0f;
       // ---- joint softmax over the 128 samples of the ray ----
       float mx = warp_max(sc);
@@ -356,8 +380,10 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
         const float zc = ((qi[8] * x + qi[9] * y) + qi[10] * z) + qi[11];
         p.a.depth_ray[(size_t)scene * p.a.R + rr] = fminf(fmaxf(zc, 0.f), 10.f);
       }
+      tacc[3] += (unsigned long long)(clock64() - tt);
       // next ray's hidden layer first: its 128x128 GEMM then runs while this ray's V sums are formed
       if (ray + (int)gridDim.x < nrays) drain_hidden(ray + gridDim.x);
+      tt = clock64();
       // ---- weighted V sums: warp `sub` covers its 32 rows, lanes cover float4 columns ----
       {
         const float *V = p.value + ((size_t)ray * 128 + sub * 32) * CAR_C_LAT;
@@ -390,6 +416,11 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
         }
       }
       rows_sync();                                       // part[], arow[], red[] reused by the next ray
+      tacc[4] += (unsigned long long)(clock64() - tt);
+    }
+    if (rec && lane == 0) {
+      tacc[5] = (unsigned long long)(clock64() - tbeg);
+      for (int i = 0; i < 6; ++i) atomicAdd(p.stats + i, tacc[i]);
     }
   }
   tc_fence_before();
@@ -427,6 +458,7 @@ int launch_tail(const car_render_args &a, int phase, int g0, int g1, const float
   TailParams p;
   p.a = a; p.g0 = g0; p.g1 = g1; p.geom = geom; p.value = value; p.q1 = q1; p.zsum = zsum;
   p.rowbias = rowbias; p.zfin = zfin;
+  p.stats = g_fused_stats ? g_fused_stats + 32 + phase * 16 : nullptr;
   p.bias_k2 = W.key2.bias; p.bias_q1 = W.qry1.bias; p.bias_q2 = W.qry2.bias; p.bias_r2 = W.rep2.bias;
   const int ops = split3 ? 2 : 1;
   const size_t tile = 2 * 128 * 128 * ops, bstage = 128 * 128 * ops;

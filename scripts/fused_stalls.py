@@ -13,7 +13,7 @@ m = CrossAttentionRenderer(n_view=2, npoints=P, precision=prec).cuda()
 m.load_state_dict(synthetic.make_state_dict(0), strict=False); m.H = m.W = H; m.pixel_val_to_cpu = False
 with torch.no_grad():
     m(inp, z=z); torch.cuda.synchronize()
-    stats = torch.zeros(32, dtype=torch.int64, device="cuda")
+    stats = torch.zeros(64, dtype=torch.int64, device="cuda")
     lib.car_debug_set_fused_stats(stats.data_ptr())
     m(inp, z=z); torch.cuda.synchronize()
     lib.car_debug_set_fused_stats(None)
@@ -26,3 +26,11 @@ print(f"precision {prec}: pair-0 rays ~{rays_pair0}")
 for k, n in names.items():
     tot = s[6] if k < 8 else s[15] if k < 16 else s[17] if k < 20 else s[21]
     print(f"  {n:18s} {100.0 * s[k] / max(1, tot):6.1f}%   {s[k] / rays_pair0:10.0f} cyc/ray")
+
+tn = ["drain(hidden)", "wait MMA (scores)", "scores", "softmax", "V sums + outputs", "TOTAL"]
+rays_cta0 = (b * H * H + 147) // 148
+for ph in (0, 1):
+    base = 32 + ph * 16
+    print(f"tail phase {'AB'[ph]} (CTA 0 row threads, {rays_cta0} rays):")
+    for i, n in enumerate(tn):
+        print(f"  {n:20s} {100.0 * s[base + i] / max(1, s[base + 5]):6.1f}%   {s[base + i] / rays_cta0:10.0f} cyc/ray")
