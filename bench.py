@@ -329,6 +329,32 @@ def main():
     roofline = roof.get(dom) or roof.get("fused") or roof.get("gemm_enc1") or roof.get("gather")
     share = {k: round(v / max(1e-9, sum(stage_ms.values())), 4) for k, v in stage_ms.items() if v > 0}
 
+    # ---- parity of what was just timed: 256 rays of scene 0 against the oracle (untimed) ----
+    parity = None
+    try:
+        from oracle import car_oracle as orc
+        idx = torch.randperm(R, generator=torch.Generator().manual_seed(0))[:256].sort().values
+        one = lambda t: t[:1].cpu()
+        inp1 = {"context": {k: one(v) for k, v in inp_h["context"].items()},
+                "query": {k: one(v) for k, v in inp_h["query"].items()}}
+        inp1["query"]["uv"] = inp1["query"]["uv"][:, :, idx]
+        z1 = [t[:2].cpu() for t in z_h]
+        cams = orc.prepare_cameras(inp1)
+        iv = torch.linspace(0, 1, P)
+        torch.set_num_threads(min(32, os.cpu_count()))
+        with torch.no_grad():
+            ref = orc.render({k: v.cpu() for k, v in sd.items()}, inp1, z1, H, H, P, interval=iv, cams=cams)
+            model._fcache = None
+            got = model.render_prepared({k: v.to(dev).contiguous() for k, v in cams.items()},
+                                        inp1["query"]["uv"][:, 0].contiguous().to(dev), iv.to(dev),
+                                        [t.to(dev) for t in z1], 1, idx.numel())
+        rgb = got["rgb"].cpu()
+        parity = {"rays": int(idx.numel()), "rgb_rel_err_vs_oracle": float((rgb - ref["rgb"]).abs().max() / ref["rgb"].abs().max()),
+                  "psnr_db_vs_oracle": orc.psnr(rgb, ref["rgb"]),
+                  "valid_mask_equal": bool(torch.equal(got["valid_mask"].cpu(), ref["valid_mask"]))}
+    except Exception as exc:  # pragma: no cover - parity is reported, never fatal for the bench line
+        parity = {"error": repr(exc)[:200]}
+
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline:
         rps, dt = cpu_oracle_rays_per_s(H, P, args.cpu_rays, 128)
@@ -348,7 +374,7 @@ def main():
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
         "roofline": roofline, "roofline_all": roof, "stage_share": share, "stage_ms_per_step":
             {k: round(v / args.steps, 3) for k, v in stage_ms.items() if v > 0},
-        "cpu_baseline": cpu_base,
+        "cpu_baseline": cpu_base, "parity": parity,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

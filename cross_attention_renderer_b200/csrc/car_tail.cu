@@ -231,11 +231,16 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
     unsigned long long tacc[6] = {0, 0, 0, 0, 0, 0};     // 0 drain 1 score-wait 2 score 3 softmax 4 vsum 5 total
     const bool rec = p.stats && blockIdx.x == 0 && warp == 2;
     const long long tbeg = clock64();
-    auto write_loc = [&](int ray_l) {
+    // local_coords / clamp(pt) of a ray are fetched one ray ahead so their latency is off the critical path
+    float4 l0, l1, l2, l3, ptc_next = make_float4(0.f, 0.f, 0.f, 0.f), ptc_cur = ptc_next;
+    auto fetch_geom = [&](int ray_l) {
+      const float *Gp = p.geom + ((size_t)ray_l * 128 + row) * CAR_GEOM_STRIDE;
+      l0 = __ldg(reinterpret_cast<const float4 *>(Gp + G_LOCAL)); l1 = __ldg(reinterpret_cast<const float4 *>(Gp + G_LOCAL + 4));
+      l2 = __ldg(reinterpret_cast<const float4 *>(Gp + G_LOCAL + 8)); l3 = __ldg(reinterpret_cast<const float4 *>(Gp + G_LOCAL + 12));
+      if (PHASE == 0) { ptc_next.x = __ldg(Gp + G_PTC); ptc_next.y = __ldg(Gp + G_PTC + 1); ptc_next.z = __ldg(Gp + G_PTC + 2); }
+    };
+    auto write_loc = [&]() {
       // local_coords (16 fp32) -> bf16 hi(+lo), first 32 bytes of this row of the at1 tile (K-block 0)
-      const float *L = p.geom + ((size_t)ray_l * 128 + row) * CAR_GEOM_STRIDE + G_LOCAL;
-      const float4 l0 = *reinterpret_cast<const float4 *>(L), l1 = *reinterpret_cast<const float4 *>(L + 4);
-      const float4 l2 = *reinterpret_cast<const float4 *>(L + 8), l3 = *reinterpret_cast<const float4 *>(L + 12);
       uint32_t hi[8], lo[8];
       split2<SPLIT == 3>(l0.x, l0.y, hi[0], lo[0]); split2<SPLIT == 3>(l0.z, l0.w, hi[1], lo[1]);
       split2<SPLIT == 3>(l1.x, l1.y, hi[2], lo[2]); split2<SPLIT == 3>(l1.z, l1.w, hi[3], lo[3]);
@@ -253,7 +258,7 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
     };
     // hidden layer: accT -> (+bias | +row bias) -> ReLU -> bf16 hi/lo -> at1 (A operand of the 128x128 layer)
     auto drain_hidden = [&](int ray_l) {
-      const long long td = clock64();
+      const long long td = rec ? clock64() : 0;
       mbar_wait(t_full, tq & 1); ++tq;
       tc_fence_after();
       {
@@ -283,19 +288,25 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
         __syncwarp();
         if (lane == 0) mbar_arrive(hid_full);
       }
-      tacc[0] += (unsigned long long)(clock64() - td);
+      if (rec) tacc[0] += (unsigned long long)(clock64() - td);
     };
-    if ((int)blockIdx.x < nrays) { write_loc(blockIdx.x); drain_hidden(blockIdx.x); }
+    if ((int)blockIdx.x < nrays) {
+      fetch_geom(blockIdx.x);
+      write_loc();
+      ptc_cur = ptc_next;
+      if ((int)(blockIdx.x + gridDim.x) < nrays) fetch_geom(blockIdx.x + gridDim.x);
+      drain_hidden(blockIdx.x);
+    }
     for (int ray = blockIdx.x; ray < nrays; ray += gridDim.x, ++it) {
       const int g = p.g0 + ray, scene = g / p.a.R, rr = g - scene * p.a.R;
       const size_t grow = (size_t)ray * 128 + row;
       // ---- scores: <K,Q1> (phase A) or <Q2,Q1> (phase B), each thread its own row ----
       float sc = 0.f;
-      long long tt = clock64();
+      long long tt = rec ? clock64() : 0;
       if (PHASE == 0) { mbar_wait(k_full, it & 1); }
       mbar_wait(t_full, tq & 1); ++tq;
       tc_fence_after();
-      tacc[1] += (unsigned long long)(clock64() - tt); tt = clock64();
+      if (rec) { tacc[1] += (unsigned long long)(clock64() - tt); tt = clock64(); }
       {
         float *q1row = p.q1 + grow * 128;
 #pragma unroll
@@ -333,8 +344,13 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(done);                  // accumulators and at1 may be reused
-      if (ray + (int)gridDim.x < nrays) write_loc(ray + gridDim.x);   // next ray's K=16 operand (at1 is free: hidden GEMM retired)
-      tacc[2] += (unsigned long long)(clock64() - tt); tt = clock64();
+      const float4 ptc = ptc_cur;
+      if (ray + (int)gridDim.x < nrays) {                 // next ray's K=16 operand (at1 is free: hidden GEMM retired)
+        write_loc();
+        ptc_cur = ptc_next;
+        if (ray + 2 * (int)gridDim.x < nrays) fetch_geom(ray + 2 * gridDim.x);
+      }
+      if (rec) { tacc[2] += (unsigned long long)(clock64() - tt); tt = clock64(); }
       sc = sc / 16.0f;
       // ---- joint softmax over the 128 samples of the ray ----
       float mx = warp_max(sc);
@@ -361,8 +377,7 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
         }
         if (lane == 0) { red[8 + sub] = bv; reinterpret_cast<int *>(red)[12 + sub] = bi; }
         // expected 3-D point (models.py:577-582)
-        const float *G = p.geom + grow * CAR_GEOM_STRIDE + G_PTC;
-        const float w0 = warp_sum(aw * G[0]), w1 = warp_sum(aw * G[1]), w2 = warp_sum(aw * G[2]);
+        const float w0 = warp_sum(aw * ptc.x), w1 = warp_sum(aw * ptc.y), w2 = warp_sum(aw * ptc.z);
         if (lane == 0) { red[16 + sub * 3] = w0; red[17 + sub * 3] = w1; red[18 + sub * 3] = w2; }
       }
       rows_sync();                                       // arow[], red[] visible
@@ -380,10 +395,10 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
         const float zc = ((qi[8] * x + qi[9] * y) + qi[10] * z) + qi[11];
         p.a.depth_ray[(size_t)scene * p.a.R + rr] = fminf(fmaxf(zc, 0.f), 10.f);
       }
-      tacc[3] += (unsigned long long)(clock64() - tt);
+      if (rec) tacc[3] += (unsigned long long)(clock64() - tt);
       // next ray's hidden layer first: its 128x128 GEMM then runs while this ray's V sums are formed
       if (ray + (int)gridDim.x < nrays) drain_hidden(ray + gridDim.x);
-      tt = clock64();
+      if (rec) tt = clock64();
       // ---- weighted V sums: warp `sub` covers its 32 rows, lanes cover float4 columns ----
       {
         const float *V = p.value + ((size_t)ray * 128 + sub * 32) * CAR_C_LAT;
@@ -416,7 +431,7 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
         }
       }
       rows_sync();                                       // part[], arow[], red[] reused by the next ray
-      tacc[4] += (unsigned long long)(clock64() - tt);
+      if (rec) tacc[4] += (unsigned long long)(clock64() - tt);
     }
     if (rec && lane == 0) {
       tacc[5] = (unsigned long long)(clock64() - tbeg);
