@@ -8,7 +8,7 @@ cross_attention_renderer_b200/csrc``).
 import ctypes as C
 import os
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 PREC_FP32_SIMT, PREC_FP32_3XBF16, PREC_BF16 = 0, 1, 2
 PRECISIONS = {"fp32_simt": PREC_FP32_SIMT, "fp32": PREC_FP32_3XBF16, "bf16": PREC_BF16}
 K_ENC = 592
@@ -64,8 +64,8 @@ SYMBOLS = {
     "car_last_error": (C.c_char_p, []),
     "car_features_bytes": (C.c_size_t, [C.c_int] * 5),
     "car_pack_features": (C.c_int, [c_fp, c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp]),
-    "car_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
-    "car_default_chunk_rays": (C.c_int, [C.c_int, C.c_int]),
+    "car_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "car_default_chunk_rays": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "car_render_forward": (C.c_int, [C.POINTER(car_render_args)]),
     "car_last_launch_count": (C.c_int, []),
     "car_profile_begin": (C.c_int, []),

@@ -64,7 +64,11 @@ struct Workspace {
   size_t bytes;
 };
 
-Workspace carve(char *base, int precision, int P, int chunk) {
+// use_fused: bit 0 fused gather+encode, bit 1 fused attention tail (effective only for tensor-core
+// precisions with P == 64); the unfused activations are then never allocated.
+Workspace carve(char *base, int precision, int P, int chunk, int use_fused) {
+  const bool fused = precision != CAR_PREC_FP32_SIMT && (use_fused & 1) && P == 64;
+  const bool tail = fused && (use_fused & 2);
   Workspace w;
   memset(&w, 0, sizeof(w));
   size_t off = 0;
@@ -74,9 +78,11 @@ Workspace carve(char *base, int precision, int P, int chunk) {
   w.overlap = (uint8_t *)take((size_t)chunk * 2);
   w.geom = (float *)take(rows * CAR_GEOM_STRIDE * 4);
   w.value = (float *)take(rows * CAR_C_LAT * 4);
-  w.key = (float *)take(rows * 128 * 4);
   w.q1 = (float *)take(rows * 128 * 4);
-  w.q2 = (float *)take(rows * 128 * 4);
+  if (!tail) {
+    w.key = (float *)take(rows * 128 * 4);
+    w.q2 = (float *)take(rows * 128 * 4);
+  }
   if (precision == CAR_PREC_FP32_SIMT) {
     w.x = (float *)take(rows * 2 * CAR_K_ENC * 4);
     w.h1 = (float *)take(rows * 2 * CAR_C_FEAT * 4);
@@ -84,19 +90,23 @@ Workspace carve(char *base, int precision, int P, int chunk) {
     w.hid = (float *)take(rows * 128 * 4);
   } else {
     bool lo = precision == CAR_PREC_FP32_3XBF16;
-    w.x_hi = (uint16_t *)take(rows * 2 * CAR_K_ENC * 2);
-    w.h1_hi = (uint16_t *)take(rows * 2 * CAR_C_FEAT * 2);
-    w.in_hi = (uint16_t *)take(rows * CAR_C_FEAT * 2);
     w.hid_hi = (uint16_t *)take(rows * 128 * 2);
-    w.loc_hi = (uint16_t *)take(rows * 16 * 2);
-    if (lo) {
-      w.x_lo = (uint16_t *)take(rows * 2 * CAR_K_ENC * 2);
-      w.h1_lo = (uint16_t *)take(rows * 2 * CAR_C_FEAT * 2);
-      w.in_lo = (uint16_t *)take(rows * CAR_C_FEAT * 2);
-      w.hid_lo = (uint16_t *)take(rows * 128 * 2);
-      w.loc_lo = (uint16_t *)take(rows * 16 * 2);
+    if (lo) w.hid_lo = (uint16_t *)take(rows * 128 * 2);
+    if (!tail) {
+      w.loc_hi = (uint16_t *)take(rows * 16 * 2);
+      if (lo) w.loc_lo = (uint16_t *)take(rows * 16 * 2);
     }
-    w.interp = (float *)take(rows * CAR_C_FEAT * 4);   // only filled when debug.interp is set
+    if (!fused) {
+      w.x_hi = (uint16_t *)take(rows * 2 * CAR_K_ENC * 2);
+      w.h1_hi = (uint16_t *)take(rows * 2 * CAR_C_FEAT * 2);
+      w.in_hi = (uint16_t *)take(rows * CAR_C_FEAT * 2);
+      if (lo) {
+        w.x_lo = (uint16_t *)take(rows * 2 * CAR_K_ENC * 2);
+        w.h1_lo = (uint16_t *)take(rows * 2 * CAR_C_FEAT * 2);
+        w.in_lo = (uint16_t *)take(rows * CAR_C_FEAT * 2);
+      }
+      w.interp = (float *)take(rows * CAR_C_FEAT * 4);   // only filled when debug.interp is set
+    }
   }
   w.zsum = (float *)take((size_t)chunk * CAR_C_LAT * 4);
   w.g = (float *)take((size_t)chunk * 128 * 4);
@@ -233,16 +243,16 @@ int car_pack_features(const float *nchw, void *nhwc, int bn, int C, int h, int w
   return 0;
 }
 
-int car_default_chunk_rays(int precision, int P) {
-  (void)precision;
-  long rows_target = 1 << 19;                 // ~0.5M sample rows per chunk
+int car_default_chunk_rays(int precision, int P, int use_fused) {
+  const bool fused = precision != CAR_PREC_FP32_SIMT && (use_fused & 1) && P == 64;
+  long rows_target = fused ? (1 << 21) : (1 << 19);   // sample rows per chunk (fused path keeps ~2.4 KB per row)
   long c = rows_target / (2 * (long)P);
   if (c < 1) c = 1;
   return (int)c;
 }
 
-size_t car_workspace_bytes(int precision, int P, int chunk_rays) {
-  return carve(nullptr, precision, P, chunk_rays).bytes;
+size_t car_workspace_bytes(int precision, int P, int chunk_rays, int use_fused) {
+  return carve(nullptr, precision, P, chunk_rays, use_fused).bytes;
 }
 
 int car_render_forward(const car_render_args *pa) {
@@ -265,12 +275,15 @@ int car_render_forward(const car_render_args *pa) {
   int dev_count = 0;
   if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) { set_error("no CUDA device (there is no CPU fallback)"); return -7; }
   // largest chunk that fits the given workspace
-  int chunk = car_default_chunk_rays(a.precision, a.P);
+  if ((a.debug.interp && (a.use_fused & 1)) || ((a.debug.key || a.debug.q2) && (a.use_fused & 2))) {
+    set_error("debug taps interp/key/q2 need the unfused stages: clear the matching use_fused bits"); return -10;
+  }
+  int chunk = car_default_chunk_rays(a.precision, a.P, a.use_fused);
   int span = a.ray_end - a.ray_begin;
   if (chunk > span) chunk = span;
-  while (chunk > 1 && carve(nullptr, a.precision, a.P, chunk).bytes > a.workspace_bytes) chunk = (chunk + 1) / 2;
-  if (carve(nullptr, a.precision, a.P, chunk).bytes > a.workspace_bytes) { set_error("workspace too small: %zu bytes", a.workspace_bytes); return -8; }
-  Workspace w = carve((char *)a.workspace, a.precision, a.P, chunk);
+  while (chunk > 1 && carve(nullptr, a.precision, a.P, chunk, a.use_fused).bytes > a.workspace_bytes) chunk = (chunk + 1) / 2;
+  if (carve(nullptr, a.precision, a.P, chunk, a.use_fused).bytes > a.workspace_bytes) { set_error("workspace too small: %zu bytes", a.workspace_bytes); return -8; }
+  Workspace w = carve((char *)a.workspace, a.precision, a.P, chunk, a.use_fused);
   cudaStream_t st = (cudaStream_t)a.stream;
 
   for (int g0 = a.ray_begin; g0 < a.ray_end; g0 += chunk) {
@@ -353,8 +366,9 @@ int sample_stage_umma(const car_render_args &a, const Workspace &w, int g0, int 
                 const UmmaOut &o) {
     return launch_gemm_umma(ah, al, lda, m.hi, m.lo, m.K, M, m.N, m.K, split3, e, o, st);
   };
-  const bool fused = (a.use_fused & 1) && a.P == 64 && W.kv_fold.hi && !a.debug.interp;
-  const bool tail = fused && (a.use_fused & 2) && !a.debug.key && !a.debug.q2;
+  const bool fused = (a.use_fused & 1) && a.P == 64;
+  const bool tail = fused && (a.use_fused & 2);
+  if (fused && !W.kv_fold.hi) { set_error("use_fused needs weights.kv_fold"); return -11; }
   if (!tail) launch_split_rows(w.geom + G_LOCAL, CAR_GEOM_STRIDE, w.loc_hi, split3 ? w.loc_lo : nullptr, rows, 16, st);
   if (fused) {
     // gather + enc1 + (enc2 ∘ [value; key1]) in one CTA-pair kernel: V and relu(key1) per sample

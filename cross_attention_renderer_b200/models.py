@@ -211,9 +211,16 @@ class CrossAttentionRenderer(nn.Module):
         feats = self._packed_features(z, feat_bf16)
         total = b * R
         g0, g1 = (0, total) if ray_range is None else ray_range
-        chunk = self.chunk_rays or lib.car_default_chunk_rays(prec, P)
+        use_fused = int(self.use_fused)
+        if debug_taps is not None:
+            want_ = debug_taps.get("_keys")
+            if want_ is None or "interp" in want_:
+                use_fused &= ~3                    # interp only exists in the unfused encoder
+            elif "key" in want_ or "q2" in want_:
+                use_fused &= ~2                    # key / q2 only exist outside the fused tail
+        chunk = self.chunk_rays or lib.car_default_chunk_rays(prec, P, use_fused)
         chunk = max(1, min(chunk, g1 - g0))
-        ws = self._workspace(lib.car_workspace_bytes(prec, P, chunk), dev)
+        ws = self._workspace(lib.car_workspace_bytes(prec, P, chunk, use_fused), dev)
         out = {
             "rgb": torch.zeros(b, 1, R, 3, device=dev),
             "valid_mask": torch.zeros(b, R, 1, device=dev),
@@ -253,7 +260,7 @@ class CrossAttentionRenderer(nn.Module):
                 debug_taps[k] = torch.zeros(*shp, device=dev)
                 setattr(a.debug, k, debug_taps[k].data_ptr())
         a.stream = torch.cuda.current_stream(dev).cuda_stream
-        a.use_fused = int(self.use_fused)
+        a.use_fused = use_fused
         with torch.cuda.device(dev):
             _lib.check(lib.car_render_forward(a), "car_render_forward")
         self.last_launch_count = lib.car_last_launch_count()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CAR_ABI_VERSION 4
+#define CAR_ABI_VERSION 5
 
 /* Arithmetic of the per-sample MLP GEMMs (everything else is fp32/fp64). */
 enum car_precision {
@@ -144,12 +144,13 @@ typedef struct car_render_args {
   car_debug debug;                /* all-NULL in production                                  */
   void *stream;                   /* cudaStream_t                                            */
   int32_t use_fused;              /* bit 0: fused gather+encode kernel, bit 1: fused per-ray
-                                     attention tail (both need P == 64; else the unfused path) */
+                                     attention tail (both need P == 64; else the unfused path).
+                                     debug.interp needs bit 0 clear, debug.key/q2 bit 1 clear.   */
 } car_render_args;
 
 /* Rays are processed in chunks of `chunk_rays`; workspace scales with the chunk. */
-size_t car_workspace_bytes(int precision, int P, int chunk_rays);
-int car_default_chunk_rays(int precision, int P);
+size_t car_workspace_bytes(int precision, int P, int chunk_rays, int use_fused);
+int car_default_chunk_rays(int precision, int P, int use_fused);
 int car_render_forward(const car_render_args *args);
 
 /* Number of kernels the last car_render_forward on this thread launched. */

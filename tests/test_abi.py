@@ -68,9 +68,12 @@ int main(void) {
 def test_sizes_and_argument_errors(lib):
     assert lib.car_features_bytes(2, 64, 64, 0, 0) == 2 * 16 * 16 * 256 * 4
     assert lib.car_features_bytes(2, 64, 64, 2, 1) == 2 * 64 * 64 * 64 * 2
-    c = lib.car_default_chunk_rays(0, 64)
+    c = lib.car_default_chunk_rays(0, 64, 0)
     assert c >= 1
-    assert lib.car_workspace_bytes(0, 64, c) > lib.car_workspace_bytes(0, 64, 1) > 0
+    assert lib.car_workspace_bytes(0, 64, c, 0) > lib.car_workspace_bytes(0, 64, 1, 0) > 0
+    # the fused path never materialises the 576-wide activations
+    assert lib.car_workspace_bytes(1, 64, 1024, 3) < lib.car_workspace_bytes(1, 64, 1024, 0) / 4
+    assert lib.car_default_chunk_rays(1, 64, 3) > lib.car_default_chunk_rays(1, 64, 0)
     a = _lib.car_render_args()
     a.abi_version = 1
     assert lib.car_render_forward(C.byref(a)) == -2
