@@ -67,8 +67,8 @@ struct Workspace {
 // use_fused: bit 0 fused gather+encode, bit 1 fused attention tail (effective only for tensor-core
 // precisions with P == 64); the unfused activations are then never allocated.
 Workspace carve(char *base, int precision, int P, int chunk, int use_fused) {
-  const bool fused = precision != CAR_PREC_FP32_SIMT && (use_fused & 1) && P == 64;
-  const bool tail = fused && (use_fused & 2);
+  const bool fused = precision != CAR_PREC_FP32_SIMT && (use_fused & 1) && P % 64 == 0;
+  const bool tail = fused && (use_fused & 2) && P == 64;
   Workspace w;
   memset(&w, 0, sizeof(w));
   size_t off = 0;
@@ -244,7 +244,7 @@ int car_pack_features(const float *nchw, void *nhwc, int bn, int C, int h, int w
 }
 
 int car_default_chunk_rays(int precision, int P, int use_fused) {
-  const bool fused = precision != CAR_PREC_FP32_SIMT && (use_fused & 1) && P == 64;
+  const bool fused = precision != CAR_PREC_FP32_SIMT && (use_fused & 1) && P % 64 == 0;
   long rows_target = fused ? (1 << 21) : (1 << 19);   // sample rows per chunk (fused path keeps ~2.4 KB per row)
   long c = rows_target / (2 * (long)P);
   if (c < 1) c = 1;
@@ -366,8 +366,8 @@ int sample_stage_umma(const car_render_args &a, const Workspace &w, int g0, int 
                 const UmmaOut &o) {
     return launch_gemm_umma(ah, al, lda, m.hi, m.lo, m.K, M, m.N, m.K, split3, e, o, st);
   };
-  const bool fused = (a.use_fused & 1) && a.P == 64;
-  const bool tail = fused && (a.use_fused & 2);
+  const bool fused = (a.use_fused & 1) && a.P % 64 == 0;
+  const bool tail = fused && (a.use_fused & 2) && a.P == 64;
   if (fused && !W.kv_fold.hi) { set_error("use_fused needs weights.kv_fold"); return -11; }
   if (!tail) launch_split_rows(w.geom + G_LOCAL, CAR_GEOM_STRIDE, w.loc_hi, split3 ? w.loc_lo : nullptr, rows, 16, st);
   if (fused) {

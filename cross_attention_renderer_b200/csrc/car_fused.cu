@@ -64,6 +64,7 @@ __device__ __forceinline__ void timed_wait(uint64_t *bar, uint32_t parity, unsig
 struct FusedParams {
   const void *feat[3];
   int H, W, R, g0, g1;
+  int P, hpr;                          // samples per line (multiple of 64) and 64-row groups per line (P / 64)
   const float *geom;                   // (rows,32) for rays [g0,g1)
   const float *bias1;                  // [576]
   const float *biasf;                  // [416]
@@ -156,7 +157,13 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int nrays = p.g1 - p.g0;
+  // work item = one 64-sample group of one ray: item -> (ray = item / hpr, group = item % hpr); CTA `rank`
+  // owns that group on context `rank`.  (Names below still say `ray` for the item index.)
+  const int nrays = (p.g1 - p.g0) * p.hpr;
+  auto row_base = [&](int item) -> size_t {
+    const int rl = item / p.hpr, gq = item - rl * p.hpr;
+    return ((size_t)rl * 2 + rank) * p.P + (size_t)gq * ROWS;
+  };
   unsigned long long lst[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   unsigned long long *st = (p.stats && pair == 0 && leader) ? lst : nullptr;
   const long long t_begin = clock64();
@@ -346,7 +353,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
       timed_wait(a3_full, rq & 1, st, 2);
       tc_fence_after();
       const long long td0 = st ? clock64() : 0;
-      const size_t grow = ((size_t)ray * 2 + rank) * ROWS + row;
+      const size_t grow = row_base(ray) + row;
       // per lane: 104 accumulator columns per MMA chunk = 3 x 32 + 8; 32 fp32 = one 128-byte line
       auto emit = [&](const uint32_t *r, int n0, int cnt) {                // cnt = 32 or 8 columns from n0
 #pragma unroll
@@ -403,7 +410,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
     auto build_taps = [&](int ray_l, int buf) {
       if (pt < ROWS * 3) {
         const int rr = pt / 3, lvl = pt - rr * 3;
-        const float *G = p.geom + (((size_t)ray_l * 2 + rank) * ROWS + rr) * CAR_GEOM_STRIDE;
+        const float *G = p.geom + (row_base(ray_l) + rr) * CAR_GEOM_STRIDE;
         const int h = lvl == 0 ? p.H / 4 : (lvl == 1 ? p.H / 2 : p.H);
         const int w = lvl == 0 ? p.W / 4 : (lvl == 1 ? p.W / 2 : p.W);
         TapEntry *tb = taps + buf * (ROWS * 3 * 2);
@@ -419,7 +426,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
     if (pair < nrays) build_taps(pair, 0);
     int it_ray = 0;
     for (int ray = pair; ray < nrays; ray += npairs, ++it_ray) {
-      const int scene = (p.g0 + ray) / p.R;
+      const int scene = (p.g0 + ray / p.hpr) / p.R;
       const int buf = it_ray & 1;
       { long long tb0 = clock64();
         asm volatile("bar.sync 1, 256;" ::: "memory");     // table[buf] complete; table[buf^1] no longer read
@@ -568,7 +575,7 @@ int launch_fused_encode(const car_render_args &a, int g0, int g1, const float *g
                         uint16_t *kh_hi, uint16_t *kh_lo, cudaStream_t st) {
   const int split3 = a.precision == CAR_PREC_FP32_3XBF16;
   const car_mat &W1 = a.weights.enc1, &F = a.weights.kv_fold;
-  if (a.P != ROWS || !F.hi || F.N != N3 || F.K != 2 * N1 || W1.N != N1 || W1.K != CAR_K_ENC) {
+  if (a.P % ROWS != 0 || a.P > 256 || !F.hi || F.N != N3 || F.K != 2 * N1 || W1.N != N1 || W1.K != CAR_K_ENC) {
     set_error("fused encode: unsupported configuration (P=%d)", a.P);
     return -20;
   }
@@ -583,6 +590,7 @@ int launch_fused_encode(const car_render_args &a, int g0, int g1, const float *g
   FusedParams p;
   for (int i = 0; i < 3; ++i) p.feat[i] = a.feat[i];
   p.H = a.H; p.W = a.W; p.R = a.R; p.g0 = g0; p.g1 = g1;
+  p.P = a.P; p.hpr = a.P / ROWS;
   p.geom = geom; p.bias1 = W1.bias; p.biasf = F.bias;
   p.value = value; p.kh_hi = kh_hi; p.kh_lo = kh_lo;
   p.stats = g_fused_stats;
@@ -599,7 +607,7 @@ int launch_fused_encode(const car_render_args &a, int g0, int g1, const float *g
   static int sms = 0;
   if (!sms) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   int pairs = sms / 2;
-  if (pairs > g1 - g0) pairs = g1 - g0;
+  if (pairs > (g1 - g0) * p.hpr) pairs = (g1 - g0) * p.hpr;
   cudaError_t e = cudaSuccess;
   prof_pre(CAR_ST_FUSED, st);
 #define CAR_LAUNCH(S, T)                                                                                    \

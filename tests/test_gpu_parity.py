@@ -361,3 +361,24 @@ def test_fused_tail_matches(precision):
         top2 = aw.topk(2, dim=-1).values
         decided = (top2[..., 0] - top2[..., 1]) > 1e-4 * top2[..., 0]
         assert torch.equal(cpu(o3["at_wt_max"])[..., 0][decided], ref["at_wt_max"][..., 0][decided])
+
+
+@pytest.mark.parametrize("P", [128, 192])
+def test_fused_encode_long_lines(P):
+    """P = 128 (BASELINE config 4) / 192: the fused encode kernel takes 64-sample groups, the
+    attention tail runs unfused."""
+    b, H, Ht = 1, 64, 10
+    inp = synthetic.make_inputs(b, H, Ht, seed=55, mode="default")
+    z = synthetic.make_features(b, H, seed=55)
+    sd = synthetic.make_state_dict(seed=55)
+    cams = orc.prepare_cameras(inp)
+    interval = torch.linspace(0, 1, P)
+    with torch.no_grad():
+        ref = orc.render(sd, inp, z, H, H, P, interval=interval, cams=cams)
+    outs = {}
+    for mode in (0, 3):
+        model = make_model(sd, P, H, precision="fp32", use_fused=mode)
+        outs[mode] = run_cuda(model, inp, z, cams=cams, interval=interval)
+        assert rel_err(cpu(outs[mode]["rgb"]), ref["rgb"]) < 1e-4, mode
+        assert torch.equal(outs[mode]["pixel_val"], ref["pixel_val"])
+    assert rel_err(cpu(outs[3]["rgb"]), cpu(outs[0]["rgb"])) < 1e-4
