@@ -21,6 +21,7 @@
 // SMEM: X ring + H ring (A operands), B ring (W1 / F slices via TMA, each CTA loads its half of
 // every N chunk), tap table.  All operand tiles are K-major, 64-byte swizzle, 32 K per stage.
 #include <math.h>
+#include <stdlib.h>
 
 #include "car_common.cuh"
 #include "car_umma.cuh"
@@ -71,6 +72,7 @@ struct FusedParams {
   float *value;                        // (rows,288) fp32
   uint16_t *kh_hi, *kh_lo;             // (rows,128) bf16: relu(key_map)
   int nb;                              // B ring depth
+  int cl;                              // cluster size: 2 (one pair) or 4 (two pairs sharing the weight loads)
   unsigned long long *stats;           // optional [32] stall counters (see timed_wait), else null
 };
 
@@ -130,7 +132,7 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t 
 }
 
 template <int SPLIT, typename FT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, 1)
 k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_constant__ CUtensorMap tm_w1_lo,
                const __grid_constant__ CUtensorMap tm_f_hi, const __grid_constant__ CUtensorMap tm_f_lo,
                FusedParams p) {
@@ -154,12 +156,27 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a3_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  // cluster = p.cl CTAs (2 or 4) = p.cl/2 CTA pairs.  A pair (consecutive cluster ranks) shares one
+  // ray and the cta_group::2 MMAs; the pairs of a cluster run in lock-step on DIFFERENT rays and share
+  // every weight K-slice: pair 0's CTAs load their halves once and TMA-multicast them to the same
+  // rank-in-pair of the other pair.
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = crank & 1;                         // role inside the pair (= context of the rows)
+  const uint32_t leader_crank = crank & ~1u;               // cluster rank of this pair's MMA-issuing CTA
   const bool leader = rank == 0;
-  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const bool loader = (crank >> 1) == 0;                   // this CTA issues the weight TMA loads
+  const uint16_t pair_mask = (uint16_t)(0x3u << leader_crank);
+  const uint16_t all_mask = (uint16_t)((1u << p.cl) - 1u);
+  const uint16_t mc_mask = p.cl == 4 ? (uint16_t)((1u << crank) | (1u << (crank + 2))) : (uint16_t)(1u << crank);
+  const int pair = (int)(blockIdx.x / p.cl) * (p.cl / 2) + (int)(crank >> 1), npairs = gridDim.x >> 1;
   // work item = one 64-sample group of one ray: item -> (ray = item / hpr, group = item % hpr); CTA `rank`
   // owns that group on context `rank`.  (Names below still say `ray` for the item index.)
   const int nrays = (p.g1 - p.g0) * p.hpr;
+  // every pair runs the same number of iterations (the pairs of a cluster share the weight ring);
+  // a pair that runs out of items repeats the last one with its stores suppressed
+  const int niter = (nrays + npairs - 1) / npairs;
+  auto item_of = [&](int itn) { const int i = pair + itn * npairs; return i < nrays ? i : nrays - 1; };
+  auto valid_of = [&](int itn) { return pair + itn * npairs < nrays; };
   auto row_base = [&](int item) -> size_t {
     const int rl = item / p.hpr, gq = item - rl * p.hpr;
     return ((size_t)rl * 2 + rank) * p.P + (size_t)gq * ROWS;
@@ -173,7 +190,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
     prefetch_tmap(&tm_f_hi);
     for (int s = 0; s < NX; ++s) { mbar_init(&x_full[s], 4);   /* 2 warps of the owning group x 2 CTAs */ mbar_init(&x_empty[s], 1); }
     for (int s = 0; s < NH; ++s) { mbar_init(&h_full[s], 4); mbar_init(&h_empty[s], 1); }
-    for (int s = 0; s < p.nb; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < p.nb; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], p.cl / 2); }
     mbar_init(a1_full, 1); mbar_init(a1_empty, 8);
     mbar_init(a3_full, 1); mbar_init(a3_empty, 8);
     fence_barrier_init();
@@ -191,7 +208,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
     // =========================== B-operand TMA producer ===========================
     if (lane == 0) {
       uint32_t bq = 0;
-      for (int ray = pair; ray < nrays; ray += npairs) {
+      for (int itn = 0; itn < niter; ++itn) {
         for (int v = 0; v < 2; ++v) {
           for (int kb = 0; kb < K1_STAGES; ++kb, ++bq) {                    // W1 K-slices
             const int s = bq % p.nb;
@@ -200,8 +217,9 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
             if (leader) mbar_expect_tx(&b_full[s], (uint32_t)(N1C * C::W1_CHUNK * C::OPS * 2));
             for (int c = 0; c < N1C; ++c) {
               const int n0 = c * N1CH + (int)rank * (N1CH / 2);
-              tma_load_2d_pair(st + c * C::W1_CHUNK, &tm_w1_hi, &b_full[s], kb * KS, n0);
-              if (SPLIT == 3) tma_load_2d_pair(st + C::B_HALF + c * C::W1_CHUNK, &tm_w1_lo, &b_full[s], kb * KS, n0);
+              if (!loader) continue;
+              tma_load_2d_pair_mc(st + c * C::W1_CHUNK, &tm_w1_hi, &b_full[s], kb * KS, n0, mc_mask);
+              if (SPLIT == 3) tma_load_2d_pair_mc(st + C::B_HALF + c * C::W1_CHUNK, &tm_w1_lo, &b_full[s], kb * KS, n0, mc_mask);
             }
           }
           for (int q = 0; q < K3_STAGES; ++q, ++bq) {                       // F_v K-slices, epilogue order
@@ -213,8 +231,9 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
             if (leader) mbar_expect_tx(&b_full[s], (uint32_t)(N3C * C::F_CHUNK * C::OPS * 2));
             for (int e = 0; e < N3C; ++e) {
               const int n0 = e * N3CH + (int)rank * (N3CH / 2);
-              tma_load_2d_pair(st + e * C::F_CHUNK, &tm_f_hi, &b_full[s], k0, n0);
-              if (SPLIT == 3) tma_load_2d_pair(st + C::B_HALF + e * C::F_CHUNK, &tm_f_lo, &b_full[s], k0, n0);
+              if (!loader) continue;
+              tma_load_2d_pair_mc(st + e * C::F_CHUNK, &tm_f_hi, &b_full[s], k0, n0, mc_mask);
+              if (SPLIT == 3) tma_load_2d_pair_mc(st + C::B_HALF + e * C::F_CHUNK, &tm_f_lo, &b_full[s], k0, n0, mc_mask);
             }
           }
         }
@@ -228,7 +247,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
     if (leader) {
       const uint32_t idesc1 = make_idesc_bf16(128, N1CH), idesc3 = make_idesc_bf16(128, N3CH);
       uint32_t bq = 0, xq = 0, hq = 0, av = 0, rq = 0;
-      for (int ray = pair; ray < nrays; ray += npairs, ++rq) {
+      for (int itn = 0; itn < niter; ++itn, ++rq) {
         for (int v = 0; v < 2; ++v, ++av) {
           timed_wait(a1_empty, (av & 1) ^ 1, st, 0);                         // acc1 drained
           tc_fence_after();
@@ -256,9 +275,9 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
                   }
                 }
               }
-              umma_commit_pair(&x_empty[sx], 0x3);
-              umma_commit_pair(&b_empty[sb], 0x3);
-              if (kb == K1_STAGES - 1) umma_commit_pair(a1_full, 0x3);
+              umma_commit_pair(&x_empty[sx], pair_mask);
+              umma_commit_pair(&b_empty[sb], all_mask);
+              if (kb == K1_STAGES - 1) umma_commit_pair(a1_full, pair_mask);
             }
             __syncwarp();
           }
@@ -286,9 +305,9 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
                   }
                 }
               }
-              umma_commit_pair(&h_empty[sh], 0x3);
-              umma_commit_pair(&b_empty[sb], 0x3);
-              if (v == 1 && q == K3_STAGES - 1) umma_commit_pair(a3_full, 0x3);
+              umma_commit_pair(&h_empty[sh], pair_mask);
+              umma_commit_pair(&b_empty[sb], all_mask);
+              if (v == 1 && q == K3_STAGES - 1) umma_commit_pair(a3_full, pair_mask);
             }
             __syncwarp();
           }
@@ -302,7 +321,9 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
     const int half = sub >> 1;                             // lanes 64..127 hold the upper half of each chunk
     const uint32_t tlane = tmem_base + ((uint32_t)(sub * 32) << 16);
     uint32_t av = 0, rq = 0, hi_count = 0;                 // hi_count: chunks this half has produced
-    for (int ray = pair; ray < nrays; ray += npairs, ++rq) {
+    for (int itn = 0; itn < niter; ++itn, ++rq) {
+      const int ray = item_of(itn);
+      const bool valid = valid_of(itn);
       for (int v = 0; v < 2; ++v, ++av) {
         timed_wait(a1_full, av & 1, st, 0);
         tc_fence_after();
@@ -341,13 +362,13 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
           fence_async_smem();
           if (st) { st[4] += (unsigned long long)(clock64() - tc0); tc0 = clock64(); }
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(&h_full[sh], 0);
+          if (lane == 0) mbar_arrive_cluster(&h_full[sh], leader_crank);
           if (st) st[5] += (unsigned long long)(clock64() - tc0);
         }
         hi_count += 9;
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(a1_empty, 0);
+        if (lane == 0) mbar_arrive_cluster(a1_empty, leader_crank);
       }
       // ---- acc3 -> V (fp32) and relu(key pre-activation) (bf16 hi/lo) ----
       timed_wait(a3_full, rq & 1, st, 2);
@@ -363,6 +384,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
           float vv[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) vv[i] = __uint_as_float(r[i0 + i]) + sbiasf[n + i];
+          if (!valid) continue;
           if (n < CAR_C_LAT) {
             float *o = p.value + grow * CAR_C_LAT + n;
             *reinterpret_cast<float4 *>(o) = make_float4(vv[0], vv[1], vv[2], vv[3]);
@@ -396,7 +418,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
       if (st) st[6] += (unsigned long long)(clock64() - td0);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(a3_empty, 0);
+      if (lane == 0) mbar_arrive_cluster(a3_empty, leader_crank);
     }
   } else {
     // =========================== gather producers (warps 6..13) ===========================
@@ -423,15 +445,15 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
         }
       }
     };
-    if (pair < nrays) build_taps(pair, 0);
-    int it_ray = 0;
-    for (int ray = pair; ray < nrays; ray += npairs, ++it_ray) {
+    build_taps(item_of(0), 0);
+    for (int it_ray = 0; it_ray < niter; ++it_ray) {
+      const int ray = item_of(it_ray);
       const int scene = (p.g0 + ray / p.hpr) / p.R;
       const int buf = it_ray & 1;
       { long long tb0 = clock64();
         asm volatile("bar.sync 1, 256;" ::: "memory");     // table[buf] complete; table[buf^1] no longer read
         if (st) st[2] += (unsigned long long)(clock64() - tb0); }
-      if (ray + npairs < nrays) build_taps(ray + npairs, buf ^ 1);
+      if (it_ray + 1 < niter) build_taps(item_of(it_ray + 1), buf ^ 1);
       const TapEntry *tb = taps + buf * (ROWS * 3 * 2);
       const float *th = tanhs + buf * (ROWS * 8);
       // this ray's 38 stages are numbered s = v*19 + kb; the group takes those with (xq0 + s) % 4 == gi
@@ -545,7 +567,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
         { const long long tf0 = st ? clock64() : 0;
           fence_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(&x_full[sx], 0);
+          if (lane == 0) mbar_arrive_cluster(&x_full[sx], leader_crank);
           if (st) st[3] += (unsigned long long)(clock64() - tf0); }
       }
     }
@@ -608,12 +630,24 @@ int launch_fused_encode(const car_render_args &a, int g0, int g1, const float *g
   if (!sms) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   int pairs = sms / 2;
   if (pairs > (g1 - g0) * p.hpr) pairs = (g1 - g0) * p.hpr;
+  static int cl_env = -1;
+  if (cl_env < 0) { const char *e_ = getenv("CAR_CLUSTER"); cl_env = e_ ? atoi(e_) : 4; if (cl_env != 2 && cl_env != 4) cl_env = 4; }
+  p.cl = cl_env;
+  if (p.cl == 4) { pairs &= ~1; if (pairs < 2) { p.cl = 2; pairs = (g1 - g0) * p.hpr < sms / 2 ? (g1 - g0) * p.hpr : sms / 2; } }
   cudaError_t e = cudaSuccess;
   prof_pre(CAR_ST_FUSED, st);
 #define CAR_LAUNCH(S, T)                                                                                    \
   do {                                                                                                      \
     e = cudaFuncSetAttribute(k_fused_encode<S, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-    if (e == cudaSuccess) k_fused_encode<S, T><<<pairs * 2, THREADS, smem, st>>>(t1h, t1l, tfh, tfl, p);      \
+    if (e == cudaSuccess) {                                                                                   \
+      cudaLaunchConfig_t cfg = {};                                                                            \
+      cfg.gridDim = dim3(pairs * 2); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st; \
+      cudaLaunchAttribute at[1];                                                                              \
+      at[0].id = cudaLaunchAttributeClusterDimension;                                                         \
+      at[0].val.clusterDim.x = p.cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                  \
+      cfg.attrs = at; cfg.numAttrs = 1;                                                                       \
+      e = cudaLaunchKernelEx(&cfg, k_fused_encode<S, T>, t1h, t1l, tfh, tfl, p);                              \
+    }                                                                                                         \
   } while (0)
   if (split3) { if (a.feat_bf16) CAR_LAUNCH(3, __nv_bfloat16); else CAR_LAUNCH(3, float); }
   else { if (a.feat_bf16) CAR_LAUNCH(1, __nv_bfloat16); else CAR_LAUNCH(1, float); }

@@ -84,6 +84,17 @@ __device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorM
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(mb)
       : "memory");
 }
+// CTA-pair + multicast form: the box is written at the same smem offset of every CTA in `mask`;
+// bytes are counted on the barrier of each destination's pair leader (cute::SM100_TMA_2SM_LOAD_MULTICAST_2D).
+__device__ __forceinline__ void tma_load_2d_pair_mc(void *smem_dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1,
+                                                    uint16_t mask) {
+  uint32_t mb = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(mb), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
