@@ -631,7 +631,7 @@ int launch_fused_encode(const car_render_args &a, int g0, int g1, const float *g
   int pairs = sms / 2;
   if (pairs > (g1 - g0) * p.hpr) pairs = (g1 - g0) * p.hpr;
   static int cl_env = -1;
-  if (cl_env < 0) { const char *e_ = getenv("CAR_CLUSTER"); cl_env = e_ ? atoi(e_) : 4; if (cl_env != 2 && cl_env != 4) cl_env = 4; }
+  if (cl_env < 0) { const char *e_ = getenv("CAR_CLUSTER"); cl_env = e_ ? atoi(e_) : 2; if (cl_env != 2 && cl_env != 4) cl_env = 2;   /* 4 = two pairs share multicast weight loads: correct, but the lock-step costs more than the L2 traffic it saves (measured 897 vs 522 ms) */ }
   p.cl = cl_env;
   if (p.cl == 4) { pairs &= ~1; if (pairs < 2) { p.cl = 2; pairs = (g1 - g0) * p.hpr < sms / 2 ? (g1 - g0) * p.hpr : sms / 2; } }
   cudaError_t e = cudaSuccess;

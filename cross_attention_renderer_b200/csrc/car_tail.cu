@@ -37,7 +37,8 @@ struct TailParams {
   int g0, g1;
   const float *geom;                  // (rows,32)
   const float *value;                 // (rows,288) fp32
-  float *q1;                          // (rows,128) fp32: written in phase A, read in phase B
+  float *q1;                          // per ray [128 cols][128 rows] fp32 (column-major so that the one-row-per-lane
+                                      // accesses coalesce): written in phase A, read in phase B
   float *zsum;                        // (rays,288)
   const float *rowbias;               // (rays,128)  phase B
   float *zfin;                        // (rays,288)  phase B
@@ -308,7 +309,7 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
       tc_fence_after();
       if (rec) { tacc[1] += (unsigned long long)(clock64() - tt); tt = clock64(); }
       {
-        float *q1row = p.q1 + grow * 128;
+        float *q1col = p.q1 + (size_t)ray * 128 * 128 + row;      // element (col c, this row) at q1col[c * 128]
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint32_t rt_[32], rk[32];
@@ -325,13 +326,15 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
                 k4[e] = __uint_as_float(rk[i + e]) + __ldg(p.bias_k2 + j * 32 + i + e);
                 sc = fmaf(k4[e], q[e], sc);
               }
-              *reinterpret_cast<float4 *>(q1row + j * 32 + i) = make_float4(q[0], q[1], q[2], q[3]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) q1col[(size_t)(j * 32 + i + e) * 128] = q[e];
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 q = *reinterpret_cast<const float4 *>(q1row + j * 32 + i);
-              const float qq[4] = {q.x, q.y, q.z, q.w};
+              float qq[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) qq[e] = q1col[(size_t)(j * 32 + i + e) * 128];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float x = __uint_as_float(rt_[i + e]) + __ldg(p.bias_r2 + j * 32 + i + e);
@@ -403,16 +406,22 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
       {
         const float *V = p.value + ((size_t)ray * 128 + sub * 32) * CAR_C_LAT;
         float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0, acc2 = acc0;
-#pragma unroll 8
-        for (int i = 0; i < 32; ++i) {
-          const float a = arow[sub * 32 + i];
-          const float4 *vr = reinterpret_cast<const float4 *>(V + (size_t)i * CAR_C_LAT);
-          const float4 v0 = __ldg(vr + lane), v1 = __ldg(vr + 32 + lane);
-          acc0.x = fmaf(a, v0.x, acc0.x); acc0.y = fmaf(a, v0.y, acc0.y); acc0.z = fmaf(a, v0.z, acc0.z); acc0.w = fmaf(a, v0.w, acc0.w);
-          acc1.x = fmaf(a, v1.x, acc1.x); acc1.y = fmaf(a, v1.y, acc1.y); acc1.z = fmaf(a, v1.z, acc1.z); acc1.w = fmaf(a, v1.w, acc1.w);
-          if (lane < 8) {
-            const float4 v2 = __ldg(vr + 64 + lane);
-            acc2.x = fmaf(a, v2.x, acc2.x); acc2.y = fmaf(a, v2.y, acc2.y); acc2.z = fmaf(a, v2.z, acc2.z); acc2.w = fmaf(a, v2.w, acc2.w);
+        const int l2 = lane < 8 ? 64 + lane : lane;                  // third float4 column only exists for lanes 0..7
+        const float m2 = lane < 8 ? 1.f : 0.f;
+#pragma unroll 1
+        for (int i0 = 0; i0 < 32; i0 += 8) {
+          float4 v0[8], v1[8], v2[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {                              // 24 independent 512-byte warp loads in flight
+            const float4 *vr = reinterpret_cast<const float4 *>(V + (size_t)(i0 + i) * CAR_C_LAT);
+            v0[i] = __ldg(vr + lane); v1[i] = __ldg(vr + 32 + lane); v2[i] = __ldg(vr + l2);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float a = arow[sub * 32 + i0 + i], a2 = a * m2;
+            acc0.x = fmaf(a, v0[i].x, acc0.x); acc0.y = fmaf(a, v0[i].y, acc0.y); acc0.z = fmaf(a, v0[i].z, acc0.z); acc0.w = fmaf(a, v0[i].w, acc0.w);
+            acc1.x = fmaf(a, v1[i].x, acc1.x); acc1.y = fmaf(a, v1[i].y, acc1.y); acc1.z = fmaf(a, v1[i].z, acc1.z); acc1.w = fmaf(a, v1[i].w, acc1.w);
+            acc2.x = fmaf(a2, v2[i].x, acc2.x); acc2.y = fmaf(a2, v2[i].y, acc2.y); acc2.z = fmaf(a2, v2[i].z, acc2.z); acc2.w = fmaf(a2, v2[i].w, acc2.w);
           }
         }
         float4 *pp = reinterpret_cast<float4 *>(part + sub * CAR_C_LAT);

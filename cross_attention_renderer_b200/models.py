@@ -216,8 +216,8 @@ class CrossAttentionRenderer(nn.Module):
             want_ = debug_taps.get("_keys")
             if want_ is None or "interp" in want_:
                 use_fused &= ~3                    # interp only exists in the unfused encoder
-            elif "key" in want_ or "q2" in want_:
-                use_fused &= ~2                    # key / q2 only exist outside the fused tail
+            elif "key" in want_ or "q2" in want_ or "q1" in want_:
+                use_fused &= ~2                    # key / q2 / row-major q1 only exist outside the fused tail
         chunk = self.chunk_rays or lib.car_default_chunk_rays(prec, P, use_fused)
         chunk = max(1, min(chunk, g1 - g0))
         ws = self._workspace(lib.car_workspace_bytes(prec, P, chunk, use_fused), dev)
