@@ -8,14 +8,14 @@ cross_attention_renderer_b200/csrc``).
 import ctypes as C
 import os
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 PREC_FP32_SIMT, PREC_FP32_3XBF16, PREC_BF16 = 0, 1, 2
 PRECISIONS = {"fp32_simt": PREC_FP32_SIMT, "fp32": PREC_FP32_3XBF16, "bf16": PREC_BF16}
 K_ENC = 592
 GEOM_STRIDE = 32
 
 STAGES = ("raysetup", "sample_geom", "gather", "gemm_enc1", "gemm_enc2", "gemm_kv", "gemm_small",
-          "attention", "phi", "pack", "fused")
+          "attention", "phi", "pack", "fused", "backward")
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcar_b200.so")
 
@@ -55,7 +55,29 @@ class car_render_args(C.Structure):
                 ("rgb", c_fp), ("valid_mask", c_fp), ("depth_ray", c_fp), ("at_wt", c_fp),
                 ("at_wt_max", c_fp), ("pixel_val", c_fp), ("coords", c_fp),
                 ("workspace", c_fp), ("workspace_bytes", C.c_size_t),
-                ("debug", car_debug), ("stream", c_fp), ("use_fused", C.c_int32)]
+                ("debug", car_debug), ("stream", c_fp), ("use_fused", C.c_int32),
+                ("train", C.c_int32)]
+
+
+class car_mat_grad(C.Structure):
+    _fields_ = [("w", c_fp), ("bias", c_fp)]
+
+
+GRAD_MATS = ("enc1", "enc2", "value", "key1", "key2", "qry1", "qry2", "rep1_loc", "rep1_g", "rep2",
+             "enc_lat", "phi_in")
+
+
+class car_weight_grads(C.Structure):
+    _fields_ = [(n, car_mat_grad) for n in GRAD_MATS] + [
+        ("phi_z", car_mat_grad * 3), ("phi_fc0", car_mat_grad * 3), ("phi_fc1", car_mat_grad * 3),
+        ("phi_out", car_mat_grad)]
+
+
+class car_backward_args(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("fwd", C.POINTER(car_render_args)),
+                ("d_rgb", c_fp), ("d_depth_ray", c_fp), ("grads", car_weight_grads),
+                ("d_feat", c_fp * 3), ("workspace", c_fp), ("workspace_bytes", C.c_size_t),
+                ("stream", c_fp)]
 
 
 # every symbol include/car_b200.h declares: (restype, argtypes)
@@ -67,6 +89,10 @@ SYMBOLS = {
     "car_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "car_default_chunk_rays": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "car_render_forward": (C.c_int, [C.POINTER(car_render_args)]),
+    "car_train_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "car_backward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "car_render_backward": (C.c_int, [C.POINTER(car_backward_args)]),
+    "car_unpack_features": (C.c_int, [c_fp, c_fp, C.c_int, C.c_int, C.c_int, C.c_int, c_fp]),
     "car_last_launch_count": (C.c_int, []),
     "car_profile_begin": (C.c_int, []),
     "car_profile_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]),

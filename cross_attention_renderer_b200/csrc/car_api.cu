@@ -46,27 +46,12 @@ void prof_post(cudaStream_t st) {
   cudaEventRecord(g_prof->back().b, st);
 }
 
-namespace {
-
-size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
-
-// Workspace carve-up for one chunk.
-struct Workspace {
-  RaySeg *seg; uint8_t *overlap;
-  float *geom;
-  // fp32 SIMT path
-  float *x, *h1, *interp, *value, *hid, *key, *q1, *q2;
-  // tensor-core path (bf16 hi/lo operand copies)
-  uint16_t *x_hi, *x_lo, *h1_hi, *h1_lo, *in_hi, *in_lo, *hid_hi, *hid_lo, *loc_hi, *loc_lo;
-  // per ray
-  float *zsum, *g, *rowbias, *zfin, *c18, *px, *pnet, *rgb3;
-  uint16_t *pr_hi, *pr_lo;     // per-ray bf16 operand copies for the tensor-core phi: [c18 32 | zfin 288 | relu(x) 128 | relu(net) 128]
-  size_t bytes;
-};
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // use_fused: bit 0 fused gather+encode, bit 1 fused attention tail (effective only for tensor-core
 // precisions with P == 64); the unfused activations are then never allocated.
-Workspace carve(char *base, int precision, int P, int chunk, int use_fused) {
+// train: keep every activation the backward pass reads in its own buffer (fp32 SIMT path).
+Workspace carve(char *base, int precision, int P, int chunk, int use_fused, int train) {
   const bool fused = precision != CAR_PREC_FP32_SIMT && (use_fused & 1) && P % 64 == 0;
   const bool tail = fused && (use_fused & 2) && P == 64;
   Workspace w;
@@ -88,6 +73,11 @@ Workspace carve(char *base, int precision, int P, int chunk, int use_fused) {
     w.h1 = (float *)take(rows * 2 * CAR_C_FEAT * 4);
     w.interp = (float *)take(rows * CAR_C_FEAT * 4);
     w.hid = (float *)take(rows * 128 * 4);
+    if (train) {
+      w.hid_q = (float *)take(rows * 128 * 4);
+      w.hid_r = (float *)take(rows * 128 * 4);
+      w.att2 = (float *)take(rows * 4);
+    }
   } else {
     bool lo = precision == CAR_PREC_FP32_3XBF16;
     w.hid_hi = (uint16_t *)take(rows * 128 * 2);
@@ -122,6 +112,8 @@ Workspace carve(char *base, int precision, int P, int chunk, int use_fused) {
   return w;
 }
 
+namespace {
+
 GemmEpi epi(const float *bias, int relu_out, int relu_in = 0, int accumulate = 0,
             const float *row_bias = nullptr, int rows_per_group = 1) {
   GemmEpi e;
@@ -155,18 +147,20 @@ void sample_stage_simt(const car_render_args &a, const Workspace &w, int g0, int
   { StageScope sc(CAR_ST_GEMM_KV);
     gemm(w.interp, CAR_C_FEAT, W.value, w.value, CAR_C_LAT, rows, epi(W.value.bias, 0), st);
     gemm(w.interp, CAR_C_FEAT, W.key1, w.hid, 128, rows, epi(W.key1.bias, 1), st); }
+  // training mode keeps the three 128-wide hidden layers apart (the backward pass reads them)
+  float *hid_q = w.hid_q ? w.hid_q : w.hid, *hid_r = w.hid_r ? w.hid_r : w.hid;
   gemm(w.hid, 128, W.key2, w.key, 128, rows, epi(W.key2.bias, 0), st);
-  gemm(w.geom + G_LOCAL, CAR_GEOM_STRIDE, W.qry1, w.hid, 128, rows, epi(W.qry1.bias, 1), st);
-  gemm(w.hid, 128, W.qry2, w.q1, 128, rows, epi(W.qry2.bias, 0), st);
+  gemm(w.geom + G_LOCAL, CAR_GEOM_STRIDE, W.qry1, hid_q, 128, rows, epi(W.qry1.bias, 1), st);
+  gemm(hid_q, 128, W.qry2, w.q1, 128, rows, epi(W.qry2.bias, 0), st);
   // A.9 round 1
   launch_attention1(a, g0, g1, w.key, w.q1, w.value, w.geom, w.zsum, nullptr, st);
   // A.10 round 2: per-ray part of query_repeat_embed becomes a row bias (models.py:548-553)
   gemm(w.zsum, CAR_C_LAT, W.enc_lat, w.g, 128, nr, epi(W.enc_lat.bias, 0), st);
   gemm(w.g, 128, W.rep1_g, w.rowbias, 128, nr, epi(W.rep1_g.bias, 0), st);
-  gemm(w.geom + G_LOCAL, CAR_GEOM_STRIDE, W.rep1_loc, w.hid, 128, rows,
+  gemm(w.geom + G_LOCAL, CAR_GEOM_STRIDE, W.rep1_loc, hid_r, 128, rows,
        epi(nullptr, 1, 0, 0, w.rowbias, 2 * a.P), st);
-  gemm(w.hid, 128, W.rep2, w.q2, 128, rows, epi(W.rep2.bias, 0), st);
-  launch_attention2(a, g0, g1, w.q2, w.q1, w.value, w.zsum, w.zfin, st);
+  gemm(hid_r, 128, W.rep2, w.q2, 128, rows, epi(W.rep2.bias, 0), st);
+  launch_attention2(a, g0, g1, w.q2, w.q1, w.value, w.zsum, w.zfin, w.att2, st);
 }
 
 // ---- per-sample stage, tcgen05 ------------------------------------------------------------
@@ -252,7 +246,11 @@ int car_default_chunk_rays(int precision, int P, int use_fused) {
 }
 
 size_t car_workspace_bytes(int precision, int P, int chunk_rays, int use_fused) {
-  return carve(nullptr, precision, P, chunk_rays, use_fused).bytes;
+  return carve(nullptr, precision, P, chunk_rays, use_fused, 0).bytes;
+}
+
+size_t car_train_workspace_bytes(int precision, int P, int rays) {
+  return carve(nullptr, precision, P, rays, 0, 1).bytes;
 }
 
 int car_render_forward(const car_render_args *pa) {
@@ -281,9 +279,21 @@ int car_render_forward(const car_render_args *pa) {
   int chunk = car_default_chunk_rays(a.precision, a.P, a.use_fused);
   int span = a.ray_end - a.ray_begin;
   if (chunk > span) chunk = span;
-  while (chunk > 1 && carve(nullptr, a.precision, a.P, chunk, a.use_fused).bytes > a.workspace_bytes) chunk = (chunk + 1) / 2;
-  if (carve(nullptr, a.precision, a.P, chunk, a.use_fused).bytes > a.workspace_bytes) { set_error("workspace too small: %zu bytes", a.workspace_bytes); return -8; }
-  Workspace w = carve((char *)a.workspace, a.precision, a.P, chunk, a.use_fused);
+  const int use_fused = a.train ? 0 : a.use_fused;
+  if (a.train) {
+    // training mode: the whole ray range is one chunk and its activations stay in the workspace
+    // for car_render_backward
+    if (a.precision != CAR_PREC_FP32_SIMT) { set_error("train=1 needs precision CAR_PREC_FP32_SIMT"); return -12; }
+    if (a.feat_bf16) { set_error("train=1 needs fp32 feature maps"); return -12; }
+    chunk = span;
+    if (carve(nullptr, a.precision, a.P, chunk, 0, 1).bytes > a.workspace_bytes) {
+      set_error("train=1: workspace must hold the whole ray range (car_train_workspace_bytes), got %zu bytes", a.workspace_bytes);
+      return -8;
+    }
+  }
+  while (chunk > 1 && carve(nullptr, a.precision, a.P, chunk, use_fused, a.train).bytes > a.workspace_bytes) chunk = (chunk + 1) / 2;
+  if (carve(nullptr, a.precision, a.P, chunk, use_fused, a.train).bytes > a.workspace_bytes) { set_error("workspace too small: %zu bytes", a.workspace_bytes); return -8; }
+  Workspace w = carve((char *)a.workspace, a.precision, a.P, chunk, use_fused, a.train);
   cudaStream_t st = (cudaStream_t)a.stream;
 
   for (int g0 = a.ray_begin; g0 < a.ray_end; g0 += chunk) {
@@ -404,7 +414,7 @@ int sample_stage_umma(const car_render_args &a, const Workspace &w, int g0, int 
   if ((rc = mm(w.loc_hi, w.loc_lo, 16, W.rep1_loc, rows, epi(nullptr, 1, 0, 0, w.rowbias, 2 * a.P),
                out_bf(w.hid_hi, w.hid_lo, 128)))) return rc;
   if ((rc = mm(w.hid_hi, w.hid_lo, 128, W.rep2, rows, epi(W.rep2.bias, 0), out_f(w.q2, 128)))) return rc;
-  launch_attention2(a, g0, g1, w.q2, w.q1, w.value, w.zsum, w.zfin, st);
+  launch_attention2(a, g0, g1, w.q2, w.q1, w.value, w.zsum, w.zfin, nullptr, st);
   return 0;
 }
 }  // namespace

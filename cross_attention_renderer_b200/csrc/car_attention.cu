@@ -112,13 +112,15 @@ k_attention1(car_render_args a, int g0, const float *__restrict__ key,
 __global__ void __launch_bounds__(ATT_THREADS)
 k_attention2(car_render_args a, int g0, const float *__restrict__ q2, const float *__restrict__ q1,
              const float *__restrict__ value, const float *__restrict__ zsum,
-             float *__restrict__ zfin) {
+             float *__restrict__ zfin, float *__restrict__ att2) {
   __shared__ float sc[MAX_ROWS];
   __shared__ float red[8];
   int gl = blockIdx.x;
   int P = a.P, rows = 2 * P;
   size_t row0 = (size_t)gl * rows;
   scores_softmax(q2 + row0 * 128, q1 + row0 * 128, rows, sc, red);
+  if (att2)                                     // training mode: round-2 weights for the backward pass
+    for (int i = threadIdx.x; i < rows; i += ATT_THREADS) att2[row0 + i] = sc[i];
   // per ctx: sum_k a2*V + z_sum, then summed over ctx (models.py:561-564)
   for (int c = threadIdx.x; c < CAR_C_LAT; c += ATT_THREADS) {
     const float *v = value + row0 * CAR_C_LAT + c;
@@ -170,10 +172,10 @@ void launch_attention1(const car_render_args &a, int g0, int g1, const float *ke
 }
 
 void launch_attention2(const car_render_args &a, int g0, int g1, const float *q2, const float *q1,
-                       const float *value, const float *zsum, float *zfin, cudaStream_t st) {
+                       const float *value, const float *zsum, float *zfin, float *att2, cudaStream_t st) {
   if (g1 <= g0) return;
   prof_pre(CAR_ST_ATTENTION, st);
-  k_attention2<<<g1 - g0, ATT_THREADS, 0, st>>>(a, g0, q2, q1, value, zsum, zfin);
+  k_attention2<<<g1 - g0, ATT_THREADS, 0, st>>>(a, g0, q2, q1, value, zsum, zfin, att2);
   prof_post(st);
   count_launch();
 }

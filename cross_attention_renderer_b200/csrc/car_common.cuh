@@ -63,16 +63,24 @@ struct GemmEpi {
   int relu_in;              // apply relu to A on load
   int relu_out;             // tcgen05 GEMM: 2 = ReLU only on the bf16 operand copy, fp32 output stays linear
   int accumulate;           // C += result
+  const float *mask = nullptr;   // backward: result *= (mask[m][n] > 0) before accumulate (ReLU subgradient)
+  int ldmask = 0;
 };
 void launch_gemm_simt(const float *A, int lda, const float *W, int ldw, float *C, int ldc, int M,
                       int N, int K, const GemmEpi &epi, cudaStream_t st);
+
+// dW[N][K] += dY[M][N]^T · act(A[M][K]),  db[N] += column sums of dY  (exact fp32, atomics)
+void launch_wgrad_simt(const float *dY, int ldy, const float *A, int lda, float *dW, int ldw, float *db,
+                       int M, int N, int K, int relu_a, cudaStream_t st);
+// dst[C][R] = src[R][C]^T   (small weight matrices)
+void launch_transpose(const float *src, int rows, int cols, int ld_src, float *dst, cudaStream_t st);
 
 // ---- car_attention.cu ------------------------------------------------------
 void launch_attention1(const car_render_args &a, int g0, int g1, const float *key, const float *q1,
                        const float *value, const float *geom, float *zsum, float *rowbias,
                        cudaStream_t st);
 void launch_attention2(const car_render_args &a, int g0, int g1, const float *q2, const float *q1,
-                       const float *value, const float *zsum, float *zfin, cudaStream_t st);
+                       const float *value, const float *zsum, float *zfin, float *att2, cudaStream_t st);
 void launch_phi_prep(const car_render_args &a, int g0, int g1, float *c18, cudaStream_t st);
 void launch_finalize(const car_render_args &a, int g0, int g1, const float *rgb3,
                      const uint8_t *overlap, cudaStream_t st);
@@ -96,5 +104,30 @@ int launch_fused_encode(const car_render_args &a, int g0, int g1, const float *g
 int launch_tail(const car_render_args &a, int phase, int g0, int g1, const float *geom, const float *value,
                 const uint16_t *kh_hi, const uint16_t *kh_lo, float *q1, float *zsum, const float *rowbias,
                 float *zfin, cudaStream_t st);
+
+
+// ---- car_api.cu: workspace carve-up for one ray chunk ------------------------------------
+struct Workspace {
+  RaySeg *seg; uint8_t *overlap;
+  float *geom;
+  // fp32 SIMT path
+  float *x, *h1, *interp, *value, *hid, *key, *q1, *q2;
+  // training mode (car_render_args::train): activations a backward pass needs and the
+  // inference path overwrites
+  float *hid_q, *hid_r, *att2;
+  // tensor-core path (bf16 hi/lo operand copies)
+  uint16_t *x_hi, *x_lo, *h1_hi, *h1_lo, *in_hi, *in_lo, *hid_hi, *hid_lo, *loc_hi, *loc_lo;
+  // per ray
+  float *zsum, *g, *rowbias, *zfin, *c18, *px, *pnet, *rgb3;
+  uint16_t *pr_hi, *pr_lo;     // per-ray bf16 operand copies for the tensor-core phi: [c18 32 | zfin 288 | relu(x) 128 | relu(net) 128]
+  size_t bytes;
+};
+Workspace carve(char *base, int precision, int P, int chunk, int use_fused, int train);
+
+// ---- car_backward.cu / car_gather.cu ------------------------------------------------------
+// scatter-add of d(encoder input)[row][view][576] into the packed NHWC feature-map gradients
+void launch_gather_backward(const car_render_args &a, int g0, int g1, const float *geom, const float *dx,
+                            float *const d_feat[3], cudaStream_t st);
+void launch_unpack_features(const float *nhwc, float *nchw, int bn, int C, int h, int w, cudaStream_t st);
 
 }  // namespace car

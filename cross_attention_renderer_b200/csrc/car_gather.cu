@@ -191,6 +191,74 @@ k_gather(car_render_args a, int g0, int g1, const float *__restrict__ geom, OUT 
   }
 }
 
+// ---------------------------------------------------------------------------
+// Backward of the two gathers (grid_sample backward w.r.t. the input maps,
+// ATen/native/cuda/GridSampler.cuh grid_sampler_2d_backward: safe_add_2d of
+// gOut * tap weight).  One warp per sample row; d(X)[row][view][576] is
+// scattered with 16-byte vector atomics into the NHWC gradient maps.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void scatter4(float *__restrict__ img, int C, int c, const Taps &t, float4 g) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (t.off[k] >= 0) {
+      float4 v = make_float4(g.x * t.w[k], g.y * t.w[k], g.z * t.w[k], g.w * t.w[k]);
+      atomicAdd(reinterpret_cast<float4 *>(img + (size_t)t.off[k] * C + c), v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_gather_backward(car_render_args a, int g0, int g1, const float *__restrict__ geom,
+                  const float *__restrict__ dx, float *d0, float *d1, float *d2) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  long nrows = (long)(g1 - g0) * 2 * a.P;
+  if (warp >= nrows) return;
+  int rj = warp / a.P;
+  int j = rj & 1;
+  int g = g0 + (rj >> 1);
+  int s = g / a.R;
+  const float *G = geom + (size_t)warp * CAR_GEOM_STRIDE;
+  float gx = G[G_GX], gy = G[G_GY], gxc = G[G_GXC], gyc = G[G_GYC];
+  const float *dx_own = dx + ((size_t)warp * 2 + j) * CAR_C_FEAT;
+  const float *dx_oth = dx + ((size_t)warp * 2 + (1 - j)) * CAR_C_FEAT;
+  float *dl[3] = {d0, d1, d2};
+  int chan0 = 0;
+#pragma unroll
+  for (int lvl = 0; lvl < 3; ++lvl) {
+    int C = lvl == 2 ? 64 : 256;
+    int h = lvl == 0 ? a.H / 4 : (lvl == 1 ? a.H / 2 : a.H);
+    int w = lvl == 0 ? a.W / 4 : (lvl == 1 ? a.W / 2 : a.W);
+    float *own = dl[lvl] + (size_t)(s * 2 + j) * h * w * C;
+    float *oth = dl[lvl] + (size_t)(s * 2 + (1 - j)) * h * w * C;
+    Taps to = make_taps(gx, gy, w, h, true);
+    Taps tc = make_taps(gxc, gyc, w, h, false);
+    for (int c = lane * 4; c < C; c += 128) {
+      float4 go = __ldg(reinterpret_cast<const float4 *>(dx_own + chan0 + c));
+      float4 gc = __ldg(reinterpret_cast<const float4 *>(dx_oth + chan0 + c));
+      scatter4(own, C, c, to, go);
+      scatter4(oth, C, c, tc, gc);
+    }
+    chan0 += C;
+  }
+}
+
+// NHWC fp32 -> NCHW fp32 (inverse of k_pack_features)
+__global__ void k_unpack_features(const float *__restrict__ src, float *__restrict__ dst, int C, int hw) {
+  __shared__ float tile[32][33];
+  int img = blockIdx.z;
+  int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int p = p0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (p < hw && c < C) ? src[((size_t)img * hw + p) * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, p = p0 + threadIdx.x;
+    if (c < C && p < hw) dst[((size_t)img * C + c) * hw + p] = tile[threadIdx.x][i];
+  }
+}
+
 __global__ void k_split_rows(const float *__restrict__ src, int src_stride, uint16_t *__restrict__ hi,
                              uint16_t *__restrict__ lo, long n, int width) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -222,6 +290,26 @@ void launch_pack_features(const float *nchw, void *nhwc, int bn, int C, int h, i
   prof_pre(CAR_ST_PACK, st);
   if (bf16) k_pack_features<true><<<grid, block, 0, st>>>(nchw, nhwc, C, hw);
   else k_pack_features<false><<<grid, block, 0, st>>>(nchw, nhwc, C, hw);
+  prof_post(st);
+  count_launch();
+}
+
+void launch_gather_backward(const car_render_args &a, int g0, int g1, const float *geom, const float *dx,
+                            float *const d_feat[3], cudaStream_t st) {
+  long nrows = (long)(g1 - g0) * 2 * a.P;
+  if (nrows <= 0) return;
+  unsigned blocks = (unsigned)((nrows * 32 + 255) / 256);
+  prof_pre(CAR_ST_GATHER, st);
+  k_gather_backward<<<blocks, 256, 0, st>>>(a, g0, g1, geom, dx, d_feat[0], d_feat[1], d_feat[2]);
+  prof_post(st);
+  count_launch();
+}
+
+void launch_unpack_features(const float *nhwc, float *nchw, int bn, int C, int h, int w, cudaStream_t st) {
+  int hw = h * w;
+  dim3 grid((hw + 31) / 32, (C + 31) / 32, bn), block(32, 8);
+  prof_pre(CAR_ST_PACK, st);
+  k_unpack_features<<<grid, block, 0, st>>>(nhwc, nchw, C, hw);
   prof_post(st);
   count_launch();
 }

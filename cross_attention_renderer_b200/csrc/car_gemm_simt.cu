@@ -69,6 +69,7 @@ k_gemm_simt(const float *__restrict__ A, int lda, const float *__restrict__ W, i
       if (epi.bias) v += epi.bias[n];
       if (rb) v += rb[n];
       if (epi.relu_out) v = fmaxf(v, 0.f);
+      if (epi.mask && !(epi.mask[(size_t)m * epi.ldmask + n] > 0.f)) v = 0.f;
       float *c = C + (size_t)m * ldc + n;
       if (epi.accumulate) v = *c + v;
       *c = v;
@@ -76,7 +77,124 @@ k_gemm_simt(const float *__restrict__ A, int lda, const float *__restrict__ W, i
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Weight gradient:  dW[N][K] += dY[M][N]^T · act(A[M][K]),  db[N] += column sums of dY.
+// 64x64 output tile per CTA, the M (row) range is split over gridDim.z; partial tiles are
+// combined with fp32 atomics.  Rows are read row-major (coalesced along N / K).
+// ---------------------------------------------------------------------------------------
+constexpr int WG_BN = 64, WG_BK = 64, WG_BM = 16;
+
+__device__ __forceinline__ float4 load4_guard(const float *p, int valid) {
+  if (valid >= 4 && (((uintptr_t)p) & 15) == 0) return *reinterpret_cast<const float4 *>(p);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid > 0) v.x = p[0];
+  if (valid > 1) v.y = p[1];
+  if (valid > 2) v.z = p[2];
+  if (valid > 3) v.w = p[3];
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+k_wgrad_simt(const float *__restrict__ dY, int ldy, const float *__restrict__ A, int lda,
+             float *__restrict__ dW, int ldw, float *__restrict__ db, int M, int N, int K, int relu_a,
+             int m_per_cta) {
+  __shared__ __align__(16) float Ys[WG_BM][WG_BN];
+  __shared__ __align__(16) float As[WG_BM][WG_BK];
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * WG_BN, k0 = blockIdx.y * WG_BK;
+  const int m_begin = blockIdx.z * m_per_cta;
+  const int m_end = min(M, m_begin + m_per_cta);
+  const int tx = tid & 15, ty = tid >> 4;          // tx -> 4 k columns, ty -> 4 n rows
+  const int lrow = tid >> 4, lcol = (tid & 15) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float bsum = 0.f;
+  const bool do_bias = db != nullptr && blockIdx.y == 0 && tid < WG_BN;
+  for (int m0 = m_begin; m0 < m_end; m0 += WG_BM) {
+    int r = m0 + lrow;
+    float4 y = make_float4(0.f, 0.f, 0.f, 0.f), av = y;
+    if (r < m_end) {
+      y = load4_guard(dY + (size_t)r * ldy + n0 + lcol, N - (n0 + lcol));
+      av = load4_guard(A + (size_t)r * lda + k0 + lcol, K - (k0 + lcol));
+      if (relu_a) { av.x = fmaxf(av.x, 0.f); av.y = fmaxf(av.y, 0.f); av.z = fmaxf(av.z, 0.f); av.w = fmaxf(av.w, 0.f); }
+    }
+    *reinterpret_cast<float4 *>(&Ys[lrow][lcol]) = y;
+    *reinterpret_cast<float4 *>(&As[lrow][lcol]) = av;
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < WG_BM; ++rr) {
+      float4 yv = *reinterpret_cast<const float4 *>(&Ys[rr][ty * 4]);
+      float4 aa = *reinterpret_cast<const float4 *>(&As[rr][tx * 4]);
+      float yy[4] = {yv.x, yv.y, yv.z, yv.w}, a4[4] = {aa.x, aa.y, aa.z, aa.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(yy[i], a4[j], acc[i][j]);
+    }
+    if (do_bias) {
+#pragma unroll
+      for (int rr = 0; rr < WG_BM; ++rr) bsum += Ys[rr][tid];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int n = n0 + ty * 4 + i;
+    if (n >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int k = k0 + tx * 4 + j;
+      if (k < K) atomicAdd(dW + (size_t)n * ldw + k, acc[i][j]);
+    }
+  }
+  if (do_bias && n0 + tid < N) atomicAdd(db + n0 + tid, bsum);
+}
+
+__global__ void k_transpose(const float *__restrict__ src, int rows, int cols, int ld_src,
+                            float *__restrict__ dst) {
+  __shared__ float tile[32][33];
+  int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[(size_t)r * ld_src + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) dst[(size_t)c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
 }  // namespace
+
+void launch_wgrad_simt(const float *dY, int ldy, const float *A, int lda, float *dW, int ldw, float *db,
+                       int M, int N, int K, int relu_a, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0 || !dW) return;
+  int nt = (N + WG_BN - 1) / WG_BN, kt = (K + WG_BK - 1) / WG_BK;
+  int split = (148 * 4 + nt * kt - 1) / (nt * kt);
+  int max_split = (M + 63) / 64;
+  if (split > max_split) split = max_split;
+  if (split < 1) split = 1;
+  int m_per_cta = ((M + split - 1) / split + WG_BM - 1) / WG_BM * WG_BM;
+  split = (M + m_per_cta - 1) / m_per_cta;
+  dim3 grid(nt, kt, split);
+  prof_pre(-1, st);
+  k_wgrad_simt<<<grid, 256, 0, st>>>(dY, ldy, A, lda, dW, ldw, db, M, N, K, relu_a, m_per_cta);
+  prof_post(st);
+  count_launch();
+}
+
+void launch_transpose(const float *src, int rows, int cols, int ld_src, float *dst, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return;
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  prof_pre(-1, st);
+  k_transpose<<<grid, block, 0, st>>>(src, rows, cols, ld_src, dst);
+  prof_post(st);
+  count_launch();
+}
 
 void launch_gemm_simt(const float *A, int lda, const float *W, int ldw, float *C, int ldc, int M,
                       int N, int K, const GemmEpi &epi, cudaStream_t st) {

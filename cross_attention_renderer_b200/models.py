@@ -201,26 +201,54 @@ class CrossAttentionRenderer(nn.Module):
 
     def render_prepared(self, cams, uv, interval, z, b, R, ray_range=None, debug_taps=None):
         """CUDA part of forward with the pose algebra already done (used directly by the
-        bit-exactness tests so both sides see identical 4x4 matrices)."""
+        bit-exactness tests so both sides see identical 4x4 matrices).
+
+        With autograd enabled and a weight or feature map that requires grad, the call goes
+        through ``_RenderFunction`` (training-mode forward + ``car_render_backward``): ``rgb``
+        and ``depth_ray`` are then differentiable like the reference's (training.py:92,125)."""
+        needs_grad = torch.is_grad_enabled() and debug_taps is None and (
+            any(t.requires_grad for t in z)
+            or any(p.requires_grad for n, p in self.named_parameters() if n in HOT_PATH_PARAMS))
+        if needs_grad:
+            params = dict(self.named_parameters())
+            plist = [params[n] for n in HOT_PATH_PARAMS]
+            res = _RenderFunction.apply(self, cams, uv, interval, b, R, ray_range, z[0], z[1], z[2], *plist)
+            out = dict(zip(_RenderFunction.OUT_KEYS, res))
+        else:
+            out = self._launch(cams, uv, interval, z, b, R, ray_range, debug_taps)[0]
+        out["at_wts"] = [out["at_wt"]]
+        if self.pixel_val_to_cpu:
+            out["pixel_val"] = out["pixel_val"].cpu()                   # models.py:570
+        return out
+
+    def _launch(self, cams, uv, interval, z, b, R, ray_range=None, debug_taps=None, train=False, pw=None):
+        """Fill ``car_render_args`` and enqueue ``car_render_forward``.  Returns (out, args, keep)
+        where ``keep`` holds every tensor the argument struct points to."""
         lib = _lib.load()
         dev = z[0].device
         H, W, P = self.H, self.W, self.npoints
-        prec = _lib.PRECISIONS[self.precision]
-        feat_bf16 = (self.feature_dtype == "bf16") if self.feature_dtype else (prec == _lib.PREC_BF16)
-        pw = self._packed_weights()
+        prec = _lib.PREC_FP32_SIMT if train else _lib.PRECISIONS[self.precision]
+        feat_bf16 = False if train else (
+            (self.feature_dtype == "bf16") if self.feature_dtype else (prec == _lib.PREC_BF16))
+        if pw is None:
+            pw = self._packed_weights()
         feats = self._packed_features(z, feat_bf16)
         total = b * R
         g0, g1 = (0, total) if ray_range is None else ray_range
-        use_fused = int(self.use_fused)
+        use_fused = 0 if train else int(self.use_fused)
         if debug_taps is not None:
             want_ = debug_taps.get("_keys")
             if want_ is None or "interp" in want_:
                 use_fused &= ~3                    # interp only exists in the unfused encoder
             elif "key" in want_ or "q2" in want_ or "q1" in want_:
                 use_fused &= ~2                    # key / q2 / row-major q1 only exist outside the fused tail
-        chunk = self.chunk_rays or lib.car_default_chunk_rays(prec, P, use_fused)
-        chunk = max(1, min(chunk, g1 - g0))
-        ws = self._workspace(lib.car_workspace_bytes(prec, P, chunk, use_fused), dev)
+        if train:
+            # the activations stay in this buffer until backward: it belongs to the autograd node
+            ws = torch.empty(lib.car_train_workspace_bytes(prec, P, max(1, g1 - g0)), dtype=torch.uint8, device=dev)
+        else:
+            chunk = self.chunk_rays or lib.car_default_chunk_rays(prec, P, use_fused)
+            chunk = max(1, min(chunk, g1 - g0))
+            ws = self._workspace(lib.car_workspace_bytes(prec, P, chunk, use_fused), dev)
         out = {
             "rgb": torch.zeros(b, 1, R, 3, device=dev),
             "valid_mask": torch.zeros(b, R, 1, device=dev),
@@ -261,10 +289,73 @@ class CrossAttentionRenderer(nn.Module):
                 setattr(a.debug, k, debug_taps[k].data_ptr())
         a.stream = torch.cuda.current_stream(dev).cuda_stream
         a.use_fused = use_fused
+        a.train = int(train)
         with torch.cuda.device(dev):
             _lib.check(lib.car_render_forward(a), "car_render_forward")
         self.last_launch_count = lib.car_last_launch_count()
-        out["at_wts"] = [out["at_wt"]]
-        if self.pixel_val_to_cpu:
-            out["pixel_val"] = out["pixel_val"].cpu()                   # models.py:570
-        return out
+        keep = (pw, feats, ws, cams, uv, interval)
+        return out, a, keep
+
+
+class _RenderFunction(torch.autograd.Function):
+    """Autograd node of the CUDA path: ``car_render_forward(train=1)`` /
+    ``car_render_backward`` (reference: autograd through models.py:278-621).  Differentiable
+    inputs are the three feature maps and the renderer weights; differentiable outputs are
+    ``rgb`` and ``depth_ray`` (the only ones the reference's losses read,
+    loss_functions.py:74-123)."""
+
+    OUT_KEYS = ("rgb", "depth_ray", "valid_mask", "at_wt", "at_wt_max", "pixel_val", "coords")
+
+    @staticmethod
+    def forward(ctx, model, cams, uv, interval, b, R, ray_range, z1, z2, z3, *params):
+        sd = {n: p.detach() for n, p in zip(HOT_PATH_PARAMS, params)}
+        pw = packing.PackedWeights(sd)
+        z = [z1.detach(), z2.detach(), z3.detach()]
+        out, a, keep = model._launch(cams, uv, interval, z, b, R, ray_range, train=True, pw=pw)
+        ctx.args, ctx.keep, ctx.pw = a, keep, pw
+        ctx.z_like = z
+        ctx.param_shapes = {n: p.shape for n, p in zip(HOT_PATH_PARAMS, params)}
+        res = tuple(out[k] for k in _RenderFunction.OUT_KEYS)
+        ctx.mark_non_differentiable(*res[2:])
+        ctx.save_for_backward(out["at_wt"])          # read by the round-1 attention backward
+        return res
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_depth, *_):
+        lib = _lib.load()
+        a, pw = ctx.args, ctx.pw
+        (at_wt,) = ctx.saved_tensors
+        assert at_wt.data_ptr() == a.at_wt
+        dev = ctx.z_like[0].device
+        nr = a.ray_end - a.ray_begin
+        grads = packing.PackedGrads(pw)
+        want_feat = any(ctx.needs_input_grad[7:10])
+        d_feat = [torch.zeros(t.shape[0], t.shape[2], t.shape[3], t.shape[1], device=dev) for t in ctx.z_like] \
+            if want_feat else None
+        ws = torch.empty(lib.car_backward_workspace_bytes(a.P, nr), dtype=torch.uint8, device=dev)
+        bw = _lib.car_backward_args()
+        bw.abi_version = _lib.ABI_VERSION
+        bw.fwd = C_pointer(a)
+        if d_rgb is not None:
+            d_rgb = d_rgb.contiguous().float()
+            bw.d_rgb = d_rgb.data_ptr()
+        if d_depth is not None:
+            d_depth = d_depth.contiguous().float()
+            bw.d_depth_ray = d_depth.data_ptr()
+        bw.grads = grads.c_struct()
+        if want_feat:
+            for i in range(3):
+                bw.d_feat[i] = d_feat[i].data_ptr()
+        bw.workspace, bw.workspace_bytes = ws.data_ptr(), ws.numel()
+        bw.stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _lib.check(lib.car_render_backward(bw), "car_render_backward")
+        gsd = grads.unpack(ctx.param_shapes)
+        gz = packing.unpack_feature_grads(d_feat, ctx.z_like) if want_feat else [None, None, None]
+        pgr = tuple(gsd[n] if ctx.needs_input_grad[10 + i] else None for i, n in enumerate(HOT_PATH_PARAMS))
+        return (None,) * 7 + tuple(gz) + pgr
+
+
+def C_pointer(struct):
+    import ctypes
+    return ctypes.pointer(struct)

@@ -91,6 +91,78 @@ class PackedWeights:
         return w
 
 
+class PackedGrads:
+    """Zero-initialised gradient buffers in the packed layout of ``car_weights``
+    (``car_weight_grads``), and the map back to ``state_dict`` shapes."""
+
+    def __init__(self, pw):
+        self.g = {}
+        for name, m in pw.m.items():
+            if name == "kv_fold":
+                continue
+            w = torch.zeros_like(m.f32)
+            b = None if m.bias is None else torch.zeros_like(m.bias)
+            self.g[name] = (w, b)
+
+    def c_struct(self):
+        s = _lib.car_weight_grads()
+
+        def fill(dst, name):
+            w, b = self.g[name]
+            dst.w = w.data_ptr()
+            dst.bias = b.data_ptr() if b is not None else None
+        for name in _lib.GRAD_MATS + ("phi_out",):
+            fill(getattr(s, name), name)
+        for i in range(3):
+            fill(s.phi_z[i], f"phi_z{i}")
+            fill(s.phi_fc0[i], f"phi_fc0{i}")
+            fill(s.phi_fc1[i], f"phi_fc1{i}")
+        return s
+
+    def unpack(self, shapes):
+        """-> {state_dict name: gradient tensor of that parameter's shape}.  Inverse of the
+        re-groupings PackedWeights applies (K padding, query_repeat_embed split, lin_z fold)."""
+        g = self.g
+        out = {}
+
+        def put(name, w, b):
+            out[name + ".weight"] = w.reshape(shapes[name + ".weight"])
+            if b is not None:
+                out[name + ".bias"] = b
+        put("query_encode_latent", g["enc1"][0][:, :579].contiguous(), g["enc1"][1])
+        put("query_encode_latent_2", *g["enc2"])
+        put("latent_value", *g["value"])
+        put("key_map", *g["key1"])
+        put("key_map_2", *g["key2"])
+        put("query_embed", *g["qry1"])
+        put("query_embed_2", *g["qry2"])
+        put("query_repeat_embed", torch.cat([g["rep1_g"][0], g["rep1_loc"][0]], dim=1), g["rep1_g"][1])
+        put("query_repeat_embed_2", *g["rep2"])
+        put("encode_latent", *g["enc_lat"])
+        put("phi.lin_in", g["phi_in"][0][:, :18].contiguous(), g["phi_in"][1])
+        for i in range(3):
+            wz = g[f"phi_z{i}"][0]
+            put(f"phi.lin_z.{i}", torch.cat([wz, wz], dim=1), g[f"phi_z{i}"][1])
+            put(f"phi.blocks.{i}.fc_0", *g[f"phi_fc0{i}"])
+            put(f"phi.blocks.{i}.fc_1", *g[f"phi_fc1{i}"])
+        put("phi.lin_out", *g["phi_out"])
+        return out
+
+
+def unpack_feature_grads(packed, like):
+    """Packed NHWC fp32 gradient buffers -> NCHW tensors shaped like the encoder maps."""
+    lib = _lib.load()
+    out = []
+    stream = torch.cuda.current_stream().cuda_stream
+    for o, t in zip(packed, like):
+        bn, Cc, h, w = t.shape
+        d = torch.empty(bn, Cc, h, w, dtype=torch.float32, device=o.device)
+        _lib.check(lib.car_unpack_features(o.data_ptr(), d.data_ptr(), bn, Cc, h, w, stream),
+                   "car_unpack_features")
+        out.append(d)
+    return out
+
+
 def pack_features(z, bf16=False):
     """[z1,z2,z3] NCHW fp32 (device) -> list of packed NHWC buffers via
     car_pack_features.  One-off per scene batch."""

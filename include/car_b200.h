@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CAR_ABI_VERSION 5
+#define CAR_ABI_VERSION 6
 
 /* Arithmetic of the per-sample MLP GEMMs (everything else is fp32/fp64). */
 enum car_precision {
@@ -146,6 +146,10 @@ typedef struct car_render_args {
   int32_t use_fused;              /* bit 0: fused gather+encode kernel, bit 1: fused per-ray
                                      attention tail (both need P == 64; else the unfused path).
                                      debug.interp needs bit 0 clear, debug.key/q2 bit 1 clear.   */
+  int32_t train;                  /* 1: training-mode forward (reference training.py:92): the whole
+                                     ray range is processed as one chunk on the unfused fp32 path and
+                                     every activation stays in `workspace` (>= car_train_workspace_bytes)
+                                     for car_render_backward.  Needs CAR_PREC_FP32_SIMT, fp32 maps.  */
 } car_render_args;
 
 /* Rays are processed in chunks of `chunk_rays`; workspace scales with the chunk. */
@@ -153,7 +157,53 @@ size_t car_workspace_bytes(int precision, int P, int chunk_rays, int use_fused);
 int car_default_chunk_rays(int precision, int P, int use_fused);
 int car_render_forward(const car_render_args *args);
 
-/* Number of kernels the last car_render_forward on this thread launched. */
+/* ------------------------------------------------------------------------
+ * Backward pass of the path (reference: autograd of models.py:278-621 driven by
+ * train_loss.backward(), training.py:125).  Gradients flow from the cotangents of
+ * out['rgb'] (image loss, loss_functions.py:74-80) and out['depth_ray'] (depth
+ * regulariser, :113-123) to the renderer weights and to the three feature maps; nothing
+ * upstream of the sample coordinates carries a gradient (pt / depth are detached,
+ * models.py:327-328,516, and the cameras are data).
+ *
+ * Weight gradients use the packed layout of car_weights: [N][K] fp32, K padded; bias [N],
+ * and are ACCUMULATED into (+=): the caller zeroes them, which is also how several
+ * micro-batches are summed.  The host maps them back to state_dict shapes
+ * (cross_attention_renderer_b200/packing.py::unpack_grads).  kv_fold has no gradient of
+ * its own (training runs the unfused matrices).
+ * ---------------------------------------------------------------------- */
+typedef struct car_mat_grad {
+  float *w;       /* [N][K] fp32, same shape as car_mat.f32; NULL skips */
+  float *bias;    /* [N] or NULL                                        */
+} car_mat_grad;
+
+typedef struct car_weight_grads {
+  car_mat_grad enc1, enc2, value, key1, key2, qry1, qry2, rep1_loc, rep1_g, rep2, enc_lat, phi_in;
+  car_mat_grad phi_z[3], phi_fc0[3], phi_fc1[3];
+  car_mat_grad phi_out;
+} car_weight_grads;
+
+typedef struct car_backward_args {
+  int32_t abi_version;
+  const car_render_args *fwd;     /* HOST pointer: the arguments of the train=1 forward whose
+                                     workspace still holds the activations (same ray range)    */
+  const float *d_rgb;             /* (b,1,R,3) cotangent of out['rgb'], or NULL                 */
+  const float *d_depth_ray;       /* (b,R,1)   cotangent of out['depth_ray'], or NULL           */
+  car_weight_grads grads;         /* accumulated into                                           */
+  float *d_feat[3];               /* packed NHWC fp32 (b*2,h_l,w_l,C_l) feature-map gradients,
+                                     accumulated into (scatter-add of the bilinear taps =
+                                     grid_sample backward); all NULL skips them                  */
+  void *workspace;                /* >= car_backward_workspace_bytes(P, rays)                   */
+  size_t workspace_bytes;
+  void *stream;
+} car_backward_args;
+
+size_t car_train_workspace_bytes(int precision, int P, int rays);
+size_t car_backward_workspace_bytes(int P, int rays);
+int car_render_backward(const car_backward_args *args);
+/* NHWC fp32 gradient buffer -> the NCHW layout of the encoder output (inverse of car_pack_features). */
+int car_unpack_features(const float *nhwc, float *nchw, int bn, int C, int h, int w, void *stream);
+
+/* Number of kernels the last car_render_forward / car_render_backward on this thread launched. */
 int car_last_launch_count(void);
 
 /* Per-stage device timing for bench.py: between begin and end every kernel launch of this
@@ -162,7 +212,7 @@ int car_last_launch_count(void);
  * ms[0..n) / launches[0..n) (HOST pointers) and stops recording. */
 enum car_stage { CAR_ST_RAYSETUP = 0, CAR_ST_SAMPLE_GEOM, CAR_ST_GATHER, CAR_ST_GEMM_ENC1,
                  CAR_ST_GEMM_ENC2, CAR_ST_GEMM_KV, CAR_ST_GEMM_SMALL, CAR_ST_ATTENTION,
-                 CAR_ST_PHI, CAR_ST_PACK, CAR_ST_FUSED, CAR_ST_COUNT };  /* FUSED = gather+enc1+enc2+kv in one kernel */
+                 CAR_ST_PHI, CAR_ST_PACK, CAR_ST_FUSED, CAR_ST_BACKWARD, CAR_ST_COUNT };  /* FUSED = gather+enc1+enc2+kv in one kernel */
 int car_profile_begin(void);
 int car_profile_end(float *ms, int *launches, int n);
 

@@ -543,3 +543,24 @@ def psnr(a, b):
     a = (a + 1) / 2
     b = (b + 1) / 2
     return -10.0 * math.log10(max(float(((a - b) ** 2).mean()), 1e-20))
+
+
+def render_grad(sd, inp, z, H, W, P, g_rgb=None, g_depth=None, cams=None):
+    """Gradients of  L = sum(rgb * g_rgb) + sum(depth_ray * g_depth)  w.r.t. every tensor of
+    ``sd`` and the three feature maps, by torch autograd through ``render`` — the restatement
+    of the reference's ``train_loss.backward()`` (training.py:125) for the renderer.  The
+    geometry stages run on detached exactly-rounded fp32 (no parameter lies upstream of the
+    sample coordinates; the reference detaches pt/depth, models.py:327-328,516).
+    Returns (out_dict, {name: grad}, [dz1, dz2, dz3])."""
+    sd_r = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    z_r = [t.detach().clone().requires_grad_(True) for t in z]
+    with torch.enable_grad():
+        out = render(sd_r, inp, z_r, H, W, P, cams=cams)
+        loss = 0.0
+        if g_rgb is not None:
+            loss = loss + (out["rgb"] * g_rgb).sum()
+        if g_depth is not None:
+            loss = loss + (out["depth_ray"] * g_depth).sum()
+        loss.backward()
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in sd_r.items()}
+    return out, grads, [t.grad for t in z_r]

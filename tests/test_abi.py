@@ -45,8 +45,11 @@ def test_struct_layout_matches_c(tmp_path):
 #include <stddef.h>
 #include "car_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu\\n", sizeof(car_mat), sizeof(car_weights), sizeof(car_cameras),
-         sizeof(car_debug), sizeof(car_render_args));
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(car_mat), sizeof(car_weights), sizeof(car_cameras),
+         sizeof(car_debug), sizeof(car_render_args), sizeof(car_weight_grads), sizeof(car_backward_args),
+         offsetof(car_render_args, train));
+  printf("%zu %zu %zu %zu\\n", offsetof(car_backward_args, fwd), offsetof(car_backward_args, grads),
+         offsetof(car_backward_args, d_feat), offsetof(car_backward_args, stream));
   printf("%zu %zu %zu %zu %zu %zu %zu\\n", offsetof(car_render_args, feat), offsetof(car_render_args, weights),
          offsetof(car_render_args, cams), offsetof(car_render_args, uv),
          offsetof(car_render_args, workspace_bytes), offsetof(car_render_args, stream),
@@ -57,10 +60,14 @@ int main(void) {
     subprocess.run(["gcc", "-I", os.path.join(REPO, "include"), str(probe), "-o", str(exe)], check=True)
     lines = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
     sizes = list(map(int, lines[0].split()))
-    offs = list(map(int, lines[1].split()))
+    boffs = list(map(int, lines[1].split()))
+    offs = list(map(int, lines[2].split()))
     A = _lib.car_render_args
+    B = _lib.car_backward_args
     assert sizes == [C.sizeof(_lib.car_mat), C.sizeof(_lib.car_weights), C.sizeof(_lib.car_cameras),
-                     C.sizeof(_lib.car_debug), C.sizeof(A)]
+                     C.sizeof(_lib.car_debug), C.sizeof(A), C.sizeof(_lib.car_weight_grads), C.sizeof(B),
+                     A.train.offset]
+    assert boffs == [B.fwd.offset, B.grads.offset, B.d_feat.offset, B.stream.offset]
     assert offs == [A.feat.offset, A.weights.offset, A.cams.offset, A.uv.offset,
                     A.workspace_bytes.offset, A.stream.offset, A.use_fused.offset]
 
@@ -81,6 +88,16 @@ def test_sizes_and_argument_errors(lib):
     a.abi_version = _lib.ABI_VERSION
     assert lib.car_render_forward(C.byref(a)) == -3          # sizes are all zero
     assert lib.car_render_forward(None) == -1
+    # training / backward sizing and argument checks
+    assert lib.car_train_workspace_bytes(0, 64, 192) > lib.car_workspace_bytes(0, 64, 192, 0)
+    assert lib.car_backward_workspace_bytes(64, 192) > lib.car_backward_workspace_bytes(64, 1) > 0
+    bw = _lib.car_backward_args()
+    assert lib.car_render_backward(None) == -1
+    assert lib.car_render_backward(C.byref(bw)) == -1        # no forward arguments
+    bw.fwd = C.pointer(a)
+    bw.abi_version = _lib.ABI_VERSION
+    assert lib.car_render_backward(C.byref(bw)) == -12       # forward was not a train=1 call
+    assert b"train" in lib.car_last_error()
 
 
 def test_no_cpu_fallback():
