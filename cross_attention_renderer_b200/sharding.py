@@ -76,3 +76,26 @@ def render_sharded(model, input, z, rank=None, world=None, gather=True, group=No
         out.update(gather_tiles(out, total, rank, world, group=group))
     out["ray_range"] = rng
     return out
+
+
+def average_gradients(model, group=None, average=True):
+    """Gradient exchange of the data-parallel training step (reference ``average_gradients``,
+    training.py:21-28: one all_reduce per parameter, divided by the world size).  Here every
+    gradient that exists is packed into ONE flat buffer and reduced with a single collective
+    (NVSwitch reduces in-network; one launch instead of ~60), then scattered back.
+
+    With ray-sharded rendering (each rank back-propagated a different ray range of the SAME
+    batch) pass ``average=False``: the shard gradients add up to the full-batch gradient."""
+    params = [p for p in model.parameters() if p.grad is not None]
+    if not params:
+        return 0
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat /= float(dist.get_world_size(group))
+    off = 0
+    for p in params:
+        n = p.grad.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n
+    return flat.numel()

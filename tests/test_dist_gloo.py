@@ -84,3 +84,41 @@ def test_ray_range_partition_properties():
                 assert a1 == b0
     assert list(sharding.scenes_touched(10, 25, 10)) == [1, 2]
     assert list(sharding.scenes_touched(0, 0, 10)) == []
+
+
+def _grad_worker(rank, world, port, average, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3), torch.nn.Linear(3, 2))
+        # rank-dependent gradients; the last layer has none on any rank (like the layers outside
+        # the n_view=2 branch, which never receive a gradient)
+        for i, p in enumerate(list(model.parameters())[:4]):
+            p.grad = torch.full_like(p, float((rank + 1) * (i + 1)))
+        n = sharding.average_gradients(model, average=average)
+        tot = sum(r + 1 for r in range(world)) / (world if average else 1)
+        ok = n == sum(p.numel() for p in list(model.parameters())[:4])
+        for i, p in enumerate(list(model.parameters())[:4]):
+            ok &= bool(torch.allclose(p.grad, torch.full_like(p, tot * (i + 1))))
+        ok &= all(p.grad is None for p in list(model.parameters())[4:])
+        q.put((rank, bool(ok), None))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,average", [(2, True), (3, False)])
+def test_flat_gradient_allreduce_gloo(world, average):
+    """One flat all_reduce replaces the reference's per-parameter loop (training.py:21-28)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, average, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res), res
