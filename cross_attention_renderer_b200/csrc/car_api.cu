@@ -4,6 +4,7 @@
 // enqueues the stage kernels on the caller's stream.  It replaces the body of
 // CrossAttentionRenderer.forward for n_view = 2 (reference models.py:206-621) after the
 // 4x4 pose algebra (models.py:207-211), which the Python host keeps in torch.
+#include <stdlib.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>

@@ -16,7 +16,9 @@
 //   warp 0  TMA: relu(key_map) tile and the weight K-blocks (ring)
 //   warp 1  MMA issuer (tcgen05 cta_group::1, N = 128), accumulators in TMEM
 //   warps 2-5: one thread per sample row: TMEM -> bias/ReLU -> bf16 hi/lo A operand of the next
-//           GEMM (smem, 128B swizzle), row dots, softmax (shuffles + named barrier), V sums.
+//           GEMM (smem, 128B swizzle), row dots, softmax (shuffles + named barrier).
+//   warps 6-9: attention-weighted V sums of the ray whose softmax weights were just posted
+//           (double-buffered in smem), so V traffic overlaps the next ray's scores.
 #include <math.h>
 
 #include "car_common.cuh"
@@ -29,7 +31,7 @@ int make_tmap_bf16(CUtensorMap *tm, const uint16_t *base, int rows, int K, int l
 namespace {
 using namespace ptx;
 
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;          // TMA, MMA, 4 row warps, 4 V-sum warps
 constexpr int NBMAX = 3;
 
 struct TailParams {
@@ -93,16 +95,21 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *at0 = smem;                                        // relu(key_map) tile (phase A)
-  uint8_t *at1 = at0 + (PHASE == 0 ? C::TILE : 0);            // local (first 32 B of each row) then the hidden tile
+  constexpr int Q1_BYTES = 128 * 128 * 4;                     // Q1 of one ray, [col][row] fp32 (phase B: staged by cp.async)
+  const float *q1s = reinterpret_cast<const float *>(at0);
+  uint8_t *at1 = at0 + (PHASE == 0 ? C::TILE : Q1_BYTES);     // local (first 32 B of each row) then the hidden tile
   uint8_t *bs = at1 + C::TILE;
-  float *arow = reinterpret_cast<float *>(bs + (size_t)p.nb * C::B_STAGE);   // [128] softmax weights
-  float *part = arow + 128;                                                    // [4][288] per-warp V sums
+  float *arow = reinterpret_cast<float *>(bs + (size_t)p.nb * C::B_STAGE);   // [2][128] softmax weights
+  float *part = arow + 256;                                                    // [4][288] per-warp V sums
   float *red = part + 4 * CAR_C_LAT;                                           // [32] scratch
-  uint64_t *bars = reinterpret_cast<uint64_t *>(red + 32);
+  float *vred = red + 32;                                                      // [32] scratch of the V warps
+  float *sbias = vred + 32;                                                    // [3][128] hidden / output / key biases
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sbias + 3 * 128);
   uint64_t *kh_full = bars, *kh_empty = bars + 1, *loc_full = bars + 2, *hid_full = bars + 3;
   uint64_t *t_full = bars + 4, *k_full = bars + 5, *done = bars + 6;
   uint64_t *b_full = bars + 8, *b_empty = b_full + NBMAX;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(b_empty + NBMAX);
+  uint64_t *a_full = b_empty + NBMAX, *a_empty = a_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nrays = p.g1 - p.g0;
@@ -114,7 +121,14 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
     mbar_init(kh_full, 1); mbar_init(kh_empty, 1); mbar_init(loc_full, 4); mbar_init(hid_full, 4);
     mbar_init(t_full, 1); mbar_init(k_full, 1); mbar_init(done, 4);
     for (int s = 0; s < p.nb; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 4); }
     fence_barrier_init();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 192) {
+    const int c = threadIdx.x - 64;
+    sbias[c] = PHASE == 0 ? p.bias_q1[c] : 0.f;
+    sbias[128 + c] = PHASE == 0 ? p.bias_q2[c] : p.bias_r2[c];
+    sbias[256 + c] = PHASE == 0 ? p.bias_k2[c] : 0.f;
   }
   if (warp == 1) tmem_alloc<1>(tmem_slot, 256);
   tc_fence_before();
@@ -161,10 +175,12 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
             tma_load_2d(at0 + C::TILE_HALF, &tm_kh_lo, kh_full, 0, r0);
             tma_load_2d(at0 + C::TILE_HALF + C::KB_BYTES, &tm_kh_lo, kh_full, 64, r0);
           }
+        }
+        load_w(&tm_w1_hi, &tm_w1_lo, 0);                 // K = 16 layer: columns 16..63 are OOB zero fill
+        if (PHASE == 0) {
           load_w(&tm_w0_hi, &tm_w0_lo, 0);
           load_w(&tm_w0_hi, &tm_w0_lo, 64);
         }
-        load_w(&tm_w1_hi, &tm_w1_lo, 0);                 // K = 16 layer: columns 16..63 are OOB zero fill
         load_w(&tm_w2_hi, &tm_w2_lo, 0);
         load_w(&tm_w2_hi, &tm_w2_lo, 64);
       }
@@ -200,6 +216,12 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
     for (int ray = blockIdx.x; ray < nrays; ray += gridDim.x, ++it) {
       mbar_wait(done, (it & 1) ^ 1);                     // row threads finished reading both accumulators
       tc_fence_after();
+      mbar_wait(loc_full, it & 1);
+      tc_fence_after();
+      gemm_kb(tmem_base + ACCT, smem_u32(at1), 1, true);                    // K = 16 layer (first: the row threads drain it next)
+      if (elect_one()) umma_commit(t_full);
+      __syncwarp();
+      ++tq;
       if (PHASE == 0) {
         mbar_wait(kh_full, it & 1);
         tc_fence_after();
@@ -208,12 +230,6 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
         if (elect_one()) { umma_commit(kh_empty); umma_commit(k_full); }
         __syncwarp();
       }
-      mbar_wait(loc_full, it & 1);
-      tc_fence_after();
-      gemm_kb(tmem_base + ACCT, smem_u32(at1), 1, true);                    // K = 16 layer
-      if (elect_one()) umma_commit(t_full);
-      __syncwarp();
-      ++tq;
       mbar_wait(hid_full, it & 1);
       tc_fence_after();
       gemm_kb(tmem_base + ACCT, smem_u32(at1), 4, true);
@@ -222,7 +238,7 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
       __syncwarp();
       ++tq;
     }
-  } else {
+  } else if (warp < 6) {
     // =========================== row threads (warps 2..5) ===========================
     const int sub = warp & 3;
     const int row = sub * 32 + lane;                     // 0..127: ctx = row >> 6, sample k = row & 63
@@ -233,12 +249,11 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
     const bool rec = p.stats && blockIdx.x == 0 && warp == 2;
     const long long tbeg = clock64();
     // local_coords / clamp(pt) of a ray are fetched one ray ahead so their latency is off the critical path
-    float4 l0, l1, l2, l3, ptc_next = make_float4(0.f, 0.f, 0.f, 0.f), ptc_cur = ptc_next;
+    float4 l0, l1, l2, l3;
     auto fetch_geom = [&](int ray_l) {
       const float *Gp = p.geom + ((size_t)ray_l * 128 + row) * CAR_GEOM_STRIDE;
       l0 = __ldg(reinterpret_cast<const float4 *>(Gp + G_LOCAL)); l1 = __ldg(reinterpret_cast<const float4 *>(Gp + G_LOCAL + 4));
       l2 = __ldg(reinterpret_cast<const float4 *>(Gp + G_LOCAL + 8)); l3 = __ldg(reinterpret_cast<const float4 *>(Gp + G_LOCAL + 12));
-      if (PHASE == 0) { ptc_next.x = __ldg(Gp + G_PTC); ptc_next.y = __ldg(Gp + G_PTC + 1); ptc_next.z = __ldg(Gp + G_PTC + 2); }
     };
     auto write_loc = [&]() {
       // local_coords (16 fp32) -> bf16 hi(+lo), first 32 bytes of this row of the at1 tile (K-block 0)
@@ -263,18 +278,24 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
       mbar_wait(t_full, tq & 1); ++tq;
       tc_fence_after();
       {
-        const float *hb = PHASE == 0 ? p.bias_q1 : p.rowbias + (size_t)ray_l * 128;
+        const float4 *hb4 = reinterpret_cast<const float4 *>(PHASE == 0 ? sbias : p.rowbias + (size_t)ray_l * 128);
         uint32_t r[32];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           tmem_ld32(tlane + ACCT + (uint32_t)(j * 32), r);
+          float4 hb[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) hb[i] = PHASE == 0 ? hb4[j * 8 + i] : __ldg(hb4 + j * 8 + i);
           tmem_ld_wait();
           uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float x0 = fmaxf(__uint_as_float(r[2 * i]) + __ldg(hb + j * 32 + 2 * i), 0.f);
-            const float x1 = fmaxf(__uint_as_float(r[2 * i + 1]) + __ldg(hb + j * 32 + 2 * i + 1), 0.f);
-            split2<SPLIT == 3>(x0, x1, hi[i], lo[i]);
+          for (int i = 0; i < 8; ++i) {
+            const float x0 = fmaxf(__uint_as_float(r[4 * i]) + hb[i].x, 0.f);
+            const float x1 = fmaxf(__uint_as_float(r[4 * i + 1]) + hb[i].y, 0.f);
+            const float x2 = fmaxf(__uint_as_float(r[4 * i + 2]) + hb[i].z, 0.f);
+            const float x3 = fmaxf(__uint_as_float(r[4 * i + 3]) + hb[i].w, 0.f);
+            split2<SPLIT == 3>(x0, x1, hi[2 * i], lo[2 * i]);
+            split2<SPLIT == 3>(x2, x3, hi[2 * i + 1], lo[2 * i + 1]);
           }
           uint8_t *dst = at1 + (j >> 1) * C::KB_BYTES;
 #pragma unroll
@@ -291,25 +312,36 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
       }
       if (rec) tacc[0] += (unsigned long long)(clock64() - td);
     };
+    // phase B: Q1 of a ray (64 KB, written by phase A) is staged into smem with per-thread 16-byte
+    // cp.async copies issued one ray ahead (after the barrier that ends the previous ray's reads)
+    auto stage_q1 = [&](int ray_l) {
+      const char *src = reinterpret_cast<const char *>(p.q1 + (size_t)ray_l * 128 * 128);
+      const uint32_t dst = smem_u32(at0);
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) {
+        const uint32_t o = (uint32_t)(k * 128 + rt) * 16u;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + o), "l"(src + o) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     if ((int)blockIdx.x < nrays) {
+      if (PHASE == 1) stage_q1(blockIdx.x);
       fetch_geom(blockIdx.x);
       write_loc();
-      ptc_cur = ptc_next;
       if ((int)(blockIdx.x + gridDim.x) < nrays) fetch_geom(blockIdx.x + gridDim.x);
       drain_hidden(blockIdx.x);
     }
     for (int ray = blockIdx.x; ray < nrays; ray += gridDim.x, ++it) {
-      const int g = p.g0 + ray, scene = g / p.a.R, rr = g - scene * p.a.R;
-      const size_t grow = (size_t)ray * 128 + row;
       // ---- scores: <K,Q1> (phase A) or <Q2,Q1> (phase B), each thread its own row ----
       float sc = 0.f;
       long long tt = rec ? clock64() : 0;
+      float *q1col = p.q1 + (size_t)ray * 128 * 128 + row;      // element (col c, this row) at q1col[c * 128]
       if (PHASE == 0) { mbar_wait(k_full, it & 1); }
+      else { asm volatile("cp.async.wait_group 0;" ::: "memory"); rows_sync(); }   // every thread's Q1 chunks landed
       mbar_wait(t_full, tq & 1); ++tq;
       tc_fence_after();
       if (rec) { tacc[1] += (unsigned long long)(clock64() - tt); tt = clock64(); }
       {
-        float *q1col = p.q1 + (size_t)ray * 128 * 128 + row;      // element (col c, this row) at q1col[c * 128]
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint32_t rt_[32], rk[32];
@@ -320,10 +352,13 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               float q[4], k4[4];
+              const float4 bq4 = *reinterpret_cast<const float4 *>(sbias + 128 + j * 32 + i);
+              const float4 bk4 = *reinterpret_cast<const float4 *>(sbias + 256 + j * 32 + i);
+              const float bq_[4] = {bq4.x, bq4.y, bq4.z, bq4.w}, bk_[4] = {bk4.x, bk4.y, bk4.z, bk4.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                q[e] = __uint_as_float(rt_[i + e]) + __ldg(p.bias_q2 + j * 32 + i + e);
-                k4[e] = __uint_as_float(rk[i + e]) + __ldg(p.bias_k2 + j * 32 + i + e);
+                q[e] = __uint_as_float(rt_[i + e]) + bq_[e];
+                k4[e] = __uint_as_float(rk[i + e]) + bk_[e];
                 sc = fmaf(k4[e], q[e], sc);
               }
 #pragma unroll
@@ -332,13 +367,12 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
           } else {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              float qq[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) qq[e] = q1col[(size_t)(j * 32 + i + e) * 128];
+              const float4 br4 = *reinterpret_cast<const float4 *>(sbias + 128 + j * 32 + i);
+              const float br_[4] = {br4.x, br4.y, br4.z, br4.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float x = __uint_as_float(rt_[i + e]) + __ldg(p.bias_r2 + j * 32 + i + e);
-                sc = fmaf(x, qq[e], sc);
+                const float x = __uint_as_float(rt_[i + e]) + br_[e];
+                sc = fmaf(x, q1s[(j * 32 + i + e) * 128 + row], sc);
               }
             }
           }
@@ -346,11 +380,11 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(done);                  // accumulators and at1 may be reused
-      const float4 ptc = ptc_cur;
+      if (lane == 0) {
+        mbar_arrive(done);                               // accumulators and at1 may be reused
+      }
       if (ray + (int)gridDim.x < nrays) {                 // next ray's K=16 operand (at1 is free: hidden GEMM retired)
         write_loc();
-        ptc_cur = ptc_next;
         if (ray + 2 * (int)gridDim.x < nrays) fetch_geom(ray + 2 * gridDim.x);
       }
       if (rec) { tacc[2] += (unsigned long long)(clock64() - tt); tt = clock64(); }
@@ -359,6 +393,7 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
       float mx = warp_max(sc);
       if (lane == 0) red[sub] = mx;
       rows_sync();
+      if (PHASE == 1 && ray + (int)gridDim.x < nrays) stage_q1(ray + gridDim.x);   // all four warps are past their Q1 reads
       mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
       const float e = expf(sc - mx);
       float sm = warp_sum(e);
@@ -366,70 +401,112 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
       rows_sync();
       sm = (red[4] + red[5]) + (red[6] + red[7]);
       const float aw = e / sm;
-      arow[row] = aw;
-      const int ctx = row >> 6, kk = row & 63;
+      {
+        // post the weights for the V-sum warps (double-buffered: buffer it&1 was last read two rays ago)
+        const long long tw = rec ? clock64() : 0;
+        const uint32_t buf = it & 1;
+        mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1);
+        arow[buf * 128 + row] = aw;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[buf]);
+        if (rec) tacc[4] += (unsigned long long)(clock64() - tw);
+      }
+      if (rec) tacc[3] += (unsigned long long)(clock64() - tt);
+      // next ray's hidden layer: its 128x128 GEMM then runs while the V warps sum this ray
+      if (ray + (int)gridDim.x < nrays) drain_hidden(ray + gridDim.x);
+    }
+    if (rec && lane == 0) {
+      tacc[5] = (unsigned long long)(clock64() - tbeg);
+      for (int i = 0; i < 6; ++i) atomicAdd(p.stats + i, tacc[i]);
+    }
+  } else {
+    // =========================== V-sum warps (6..9) ===========================
+    // warp vs sums rows [32 vs, 32 vs + 32) of the ray: sum_i a[i] * V[i][0..288), lanes over float4 columns
+    const int vs = warp - 6;
+    const int vt = vs * 32 + lane;
+    const bool rec = p.stats && blockIdx.x == 0 && vs == 0;
+    unsigned long long vacc[3] = {0, 0, 0};              // 0 wait weights 1 loads+fma 2 reduce+store
+    const int l2 = lane < 8 ? 64 + lane : lane;          // third float4 column only exists for lanes 0..7
+    const float m2 = lane < 8 ? 1.f : 0.f;
+    uint32_t it = 0;
+    for (int ray = blockIdx.x; ray < nrays; ray += gridDim.x, ++it) {
+      const uint32_t buf = it & 1;
+      const float *V = p.value + ((size_t)ray * 128 + vs * 32) * CAR_C_LAT;
+      const float *aw = arow + buf * 128 + vs * 32;
+      float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0, acc2 = acc0;
+      float4 v0[2][4], v1[2][4], v2[2][4];
+      auto loadb = [&](int b, int s_) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 *vr = reinterpret_cast<const float4 *>(V + (size_t)(b * 4 + i) * CAR_C_LAT);
+          v0[s_][i] = __ldg(vr + lane); v1[s_][i] = __ldg(vr + 32 + lane); v2[s_][i] = __ldg(vr + l2);
+        }
+      };
+      long long tv = rec ? clock64() : 0;
+      loadb(0, 0);
+      loadb(1, 1);
+      float ptx = 0.f, pty = 0.f, ptz = 0.f;            // clamp(pt) of row vt (phase A: expected depth)
       if (PHASE == 0) {
-        p.a.at_wt[((size_t)(scene * 2 + ctx) * p.a.R + rr) * P + kk] = aw;
-        // per-context argmax (first maximum): warp-level then across the two warps of the context
-        float bv = aw; int bi = kk;
+        const float *Gp = p.geom + ((size_t)ray * 128 + vt) * CAR_GEOM_STRIDE + G_PTC;
+        ptx = __ldg(Gp); pty = __ldg(Gp + 1); ptz = __ldg(Gp + 2);
+      }
+      mbar_wait(&a_full[buf], (it >> 1) & 1);
+      if (rec) { vacc[0] += (unsigned long long)(clock64() - tv); tv = clock64(); }
+      const int g = p.g0 + ray, scene = g / p.a.R, rr = g - scene * p.a.R;
+      if (PHASE == 0) {
+        // outputs that only need the posted weights: at_wt, per-context argmax, expected 3-D point
+        const float awr = arow[buf * 128 + vt];
+        const int ctx = vt >> 6, kk = vt & 63;
+        p.a.at_wt[((size_t)(scene * 2 + ctx) * p.a.R + rr) * P + kk] = awr;
+        float bv = awr; int bi = kk;                     // first maximum: warp-level, then across the context's two warps
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
           const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
           if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
         }
-        if (lane == 0) { red[8 + sub] = bv; reinterpret_cast<int *>(red)[12 + sub] = bi; }
-        // expected 3-D point (models.py:577-582)
-        const float w0 = warp_sum(aw * ptc.x), w1 = warp_sum(aw * ptc.y), w2 = warp_sum(aw * ptc.z);
-        if (lane == 0) { red[16 + sub * 3] = w0; red[17 + sub * 3] = w1; red[18 + sub * 3] = w2; }
+        const float w0 = warp_sum(awr * ptx), w1 = warp_sum(awr * pty), w2 = warp_sum(awr * ptz);   // models.py:577-582
+        if (lane == 0) {
+          vred[8 + vs] = bv; reinterpret_cast<int *>(vred)[12 + vs] = bi;
+          vred[16 + vs * 3] = w0; vred[17 + vs * 3] = w1; vred[18 + vs * 3] = w2;
+        }
       }
-      rows_sync();                                       // arow[], red[] visible
-      if (PHASE == 0 && rt < 2) {
-        const int c = rt;                                // context c = rows [64c, 64c+64) = subs 2c, 2c+1
-        const float v0 = red[8 + 2 * c], v1 = red[8 + 2 * c + 1];
-        const int i0 = reinterpret_cast<int *>(red)[12 + 2 * c], i1 = reinterpret_cast<int *>(red)[12 + 2 * c + 1];
-        p.a.at_wt_max[(size_t)(scene * 2 + c) * p.a.R + rr] = (v1 > v0) ? i1 : i0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const float4 a4 = *reinterpret_cast<const float4 *>(aw + b * 4);
+        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float a = av[i], a2 = a * m2;
+          const float4 x0 = v0[b & 1][i], x1 = v1[b & 1][i], x2 = v2[b & 1][i];
+          acc0.x = fmaf(a, x0.x, acc0.x); acc0.y = fmaf(a, x0.y, acc0.y); acc0.z = fmaf(a, x0.z, acc0.z); acc0.w = fmaf(a, x0.w, acc0.w);
+          acc1.x = fmaf(a, x1.x, acc1.x); acc1.y = fmaf(a, x1.y, acc1.y); acc1.z = fmaf(a, x1.z, acc1.z); acc1.w = fmaf(a, x1.w, acc1.w);
+          acc2.x = fmaf(a2, x2.x, acc2.x); acc2.y = fmaf(a2, x2.y, acc2.y); acc2.z = fmaf(a2, x2.z, acc2.z); acc2.w = fmaf(a2, x2.w, acc2.w);
+        }
+        if (b + 2 < 8) loadb(b + 2, b & 1);
       }
-      if (PHASE == 0 && rt == 2) {
-        const float x = (red[16] + red[19]) + (red[22] + red[25]);
-        const float y = (red[17] + red[20]) + (red[23] + red[26]);
-        const float z = (red[18] + red[21]) + (red[24] + red[27]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_empty[buf]);        // weights of this buffer consumed
+      if (rec) { vacc[1] += (unsigned long long)(clock64() - tv); tv = clock64(); }
+      float4 *pp = reinterpret_cast<float4 *>(part + vs * CAR_C_LAT);
+      pp[lane] = acc0; pp[32 + lane] = acc1;
+      if (lane < 8) pp[64 + lane] = acc2;
+      asm volatile("bar.sync 3, 128;" ::: "memory");
+      if (PHASE == 0 && vt < 2) {
+        const int c = vt;                                // context c = rows [64c, 64c+64) = V warps 2c, 2c+1
+        const float m0 = vred[8 + 2 * c], m1 = vred[8 + 2 * c + 1];
+        const int i0 = reinterpret_cast<int *>(vred)[12 + 2 * c], i1 = reinterpret_cast<int *>(vred)[12 + 2 * c + 1];
+        p.a.at_wt_max[(size_t)(scene * 2 + c) * p.a.R + rr] = (m1 > m0) ? i1 : i0;
+      }
+      if (PHASE == 0 && vt == 2) {
+        const float x = (vred[16] + vred[19]) + (vred[22] + vred[25]);
+        const float y = (vred[17] + vred[20]) + (vred[23] + vred[26]);
+        const float z = (vred[18] + vred[21]) + (vred[24] + vred[27]);
         const float *qi = p.a.cams.qinv + (size_t)scene * 16;
         const float zc = ((qi[8] * x + qi[9] * y) + qi[10] * z) + qi[11];
         p.a.depth_ray[(size_t)scene * p.a.R + rr] = fminf(fmaxf(zc, 0.f), 10.f);
       }
-      if (rec) tacc[3] += (unsigned long long)(clock64() - tt);
-      // next ray's hidden layer first: its 128x128 GEMM then runs while this ray's V sums are formed
-      if (ray + (int)gridDim.x < nrays) drain_hidden(ray + gridDim.x);
-      if (rec) tt = clock64();
-      // ---- weighted V sums: warp `sub` covers its 32 rows, lanes cover float4 columns ----
-      {
-        const float *V = p.value + ((size_t)ray * 128 + sub * 32) * CAR_C_LAT;
-        float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0, acc2 = acc0;
-        const int l2 = lane < 8 ? 64 + lane : lane;                  // third float4 column only exists for lanes 0..7
-        const float m2 = lane < 8 ? 1.f : 0.f;
-#pragma unroll 1
-        for (int i0 = 0; i0 < 32; i0 += 8) {
-          float4 v0[8], v1[8], v2[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {                              // 24 independent 512-byte warp loads in flight
-            const float4 *vr = reinterpret_cast<const float4 *>(V + (size_t)(i0 + i) * CAR_C_LAT);
-            v0[i] = __ldg(vr + lane); v1[i] = __ldg(vr + 32 + lane); v2[i] = __ldg(vr + l2);
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float a = arow[sub * 32 + i0 + i], a2 = a * m2;
-            acc0.x = fmaf(a, v0[i].x, acc0.x); acc0.y = fmaf(a, v0[i].y, acc0.y); acc0.z = fmaf(a, v0[i].z, acc0.z); acc0.w = fmaf(a, v0[i].w, acc0.w);
-            acc1.x = fmaf(a, v1[i].x, acc1.x); acc1.y = fmaf(a, v1[i].y, acc1.y); acc1.z = fmaf(a, v1[i].z, acc1.z); acc1.w = fmaf(a, v1[i].w, acc1.w);
-            acc2.x = fmaf(a2, v2[i].x, acc2.x); acc2.y = fmaf(a2, v2[i].y, acc2.y); acc2.z = fmaf(a2, v2[i].z, acc2.z); acc2.w = fmaf(a2, v2[i].w, acc2.w);
-          }
-        }
-        float4 *pp = reinterpret_cast<float4 *>(part + sub * CAR_C_LAT);
-        pp[lane] = acc0; pp[32 + lane] = acc1;
-        if (lane < 8) pp[64 + lane] = acc2;
-      }
-      rows_sync();
-      for (int c = rt; c < CAR_C_LAT; c += 128) {
+      for (int c = vt; c < CAR_C_LAT; c += 128) {
         const float z0 = part[0 * CAR_C_LAT + c] + part[1 * CAR_C_LAT + c];      // context 0 = rows 0..63
         const float z1 = part[2 * CAR_C_LAT + c] + part[3 * CAR_C_LAT + c];      // context 1
         if (PHASE == 0) {
@@ -439,13 +516,11 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
           p.zfin[(size_t)ray * CAR_C_LAT + c] = (z0 + zs) + (z1 + zs);           // models.py:561-564
         }
       }
-      rows_sync();                                       // part[], arow[], red[] reused by the next ray
-      if (rec) tacc[4] += (unsigned long long)(clock64() - tt);
+      asm volatile("bar.sync 3, 128;" ::: "memory");    // part[] reused by the next ray
+      if (rec) vacc[2] += (unsigned long long)(clock64() - tv);
     }
-    if (rec && lane == 0) {
-      tacc[5] = (unsigned long long)(clock64() - tbeg);
-      for (int i = 0; i < 6; ++i) atomicAdd(p.stats + i, tacc[i]);
-    }
+    if (rec && lane == 0)
+      for (int i = 0; i < 3; ++i) atomicAdd(p.stats + 8 + i, vacc[i]);
   }
   tc_fence_before();
   __syncthreads();
@@ -486,7 +561,7 @@ int launch_tail(const car_render_args &a, int phase, int g0, int g1, const float
   p.bias_k2 = W.key2.bias; p.bias_q1 = W.qry1.bias; p.bias_q2 = W.qry2.bias; p.bias_r2 = W.rep2.bias;
   const int ops = split3 ? 2 : 1;
   const size_t tile = 2 * 128 * 128 * ops, bstage = 128 * 128 * ops;
-  const size_t fixed = (phase == 0 ? 2 : 1) * tile + (128 + 4 * CAR_C_LAT + 32) * 4 + (8 + 2 * NBMAX) * 8 + 16 + 512;
+  const size_t fixed = (phase == 0 ? 2 * tile : tile + 128 * 128 * 4) + (256 + 4 * CAR_C_LAT + 64 + 3 * 128) * 4 + (12 + 2 * NBMAX) * 8 + 16 + 512;
   int nb = (int)((227 * 1024 - fixed) / bstage);
   if (nb > NBMAX) nb = NBMAX;
   if (nb < 2) { set_error("tail: not enough shared memory"); return -31; }

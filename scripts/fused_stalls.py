@@ -27,10 +27,13 @@ for k, n in names.items():
     tot = s[6] if k < 8 else s[15] if k < 16 else s[17] if k < 20 else s[21]
     print(f"  {n:18s} {100.0 * s[k] / max(1, tot):6.1f}%   {s[k] / rays_pair0:10.0f} cyc/ray")
 
-tn = ["drain(hidden)", "wait MMA (scores)", "scores", "softmax", "V sums + outputs", "TOTAL"]
+tn = ["drain(hidden)", "wait MMA (scores)", "scores", "softmax + outputs", "post weights (a_empty)", "TOTAL"]
+vn = ["V warps: wait weights", "V warps: loads + fma", "V warps: reduce + store"]
 rays_cta0 = (b * H * H + 147) // 148
 for ph in (0, 1):
     base = 32 + ph * 16
-    print(f"tail phase {'AB'[ph]} (CTA 0 row threads, {rays_cta0} rays):")
+    print(f"tail phase {'AB'[ph]} (CTA 0, {rays_cta0} rays):")
     for i, n in enumerate(tn):
-        print(f"  {n:20s} {100.0 * s[base + i] / max(1, s[base + 5]):6.1f}%   {s[base + i] / rays_cta0:10.0f} cyc/ray")
+        print(f"  {n:26s} {100.0 * s[base + i] / max(1, s[base + 5]):6.1f}%   {s[base + i] / rays_cta0:10.0f} cyc/ray")
+    for i, n in enumerate(vn):
+        print(f"  {n:26s} {100.0 * s[base + 8 + i] / max(1, s[base + 5]):6.1f}%   {s[base + 8 + i] / rays_cta0:10.0f} cyc/ray")
