@@ -165,6 +165,8 @@ def main():
     ap.add_argument("--cpu-rays", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-stage-profile", action="store_true", help="diagnostic: no per-kernel events in the timed region")
+    ap.add_argument("--chunk-rays", type=int, default=0, help="diagnostic: rays per workspace chunk (0 = library default)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -199,6 +201,8 @@ def main():
     model = CrossAttentionRenderer(n_view=2, npoints=P, precision=args.precision).to(dev)
     model.load_state_dict(sd, strict=False)
     model.H = model.W = H
+    if args.chunk_rays:
+        model.chunk_rays = args.chunk_rays
     model.pixel_val_to_cpu = False          # metric excludes the optional pixel_val D2H
     inp_d = synthetic.to_device(inp_h, dev)
     z_d = [t.to(dev) for t in z_h]
@@ -229,7 +233,8 @@ def main():
     nst = len(_lib.STAGES)
     import ctypes as C
     ms_arr, ln_arr = (C.c_float * nst)(), (C.c_int * nst)()
-    lib.car_profile_begin()
+    if not args.no_stage_profile:
+        lib.car_profile_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     ev0.record()
@@ -238,7 +243,8 @@ def main():
     ev1.record()
     sync_all()
     ms_total = ev0.elapsed_time(ev1)
-    lib.car_profile_end(ms_arr, ln_arr, nst)
+    if not args.no_stage_profile:
+        lib.car_profile_end(ms_arr, ln_arr, nst)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total], device=dev)
     if world > 1:

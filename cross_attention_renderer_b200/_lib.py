@@ -17,7 +17,7 @@ GEOM_STRIDE = 32
 STAGES = ("raysetup", "sample_geom", "gather", "gemm_enc1", "gemm_enc2", "gemm_kv", "gemm_small",
           "attention", "phi", "pack", "fused", "backward")
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcar_b200.so")
+_LIB_PATH = os.environ.get("CAR_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcar_b200.so")
 
 c_fp = C.c_void_p
 

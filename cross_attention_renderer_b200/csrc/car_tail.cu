@@ -31,6 +31,11 @@ int make_tmap_bf16(CUtensorMap *tm, const uint16_t *base, int rows, int K, int l
 namespace {
 using namespace ptx;
 
+// L2 prefetch of the next ray's V / Q1 (cp.async.bulk.prefetch.L2) doubled the DRAM reads of both phases
+// (ncu: 456 / 429 KB per ray against 291 / 220 KB algorithmic, L2 hit rate 13-20 %): off.
+#ifndef TAIL_PREFETCH
+#define TAIL_PREFETCH 0
+#endif
 constexpr int THREADS = 320;          // TMA, MMA, 4 row warps, 4 V-sum warps
 constexpr int NBMAX = 3;
 
@@ -151,6 +156,7 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
         ++bq;
       };
       for (int ray = blockIdx.x; ray < nrays; ray += gridDim.x, ++it) {
+#if TAIL_PREFETCH
         {
           // pull the next ray's V rows (and Q1 rows in phase B) into L2 ahead of the row threads
           const int nx = ray + (it == 0 ? 0 : (int)gridDim.x);
@@ -165,6 +171,7 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
             }
           }
         }
+#endif
         if (PHASE == 0) {
           mbar_wait(kh_empty, (it & 1) ^ 1);
           mbar_expect_tx(kh_full, (uint32_t)C::TILE);

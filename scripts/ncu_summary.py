@@ -1,10 +1,9 @@
-"""Summarise an .ncu-rep (one kernel) into the handful of numbers DESIGN.md / bench.py cite."""
+"""Summarise an .ncu-rep (one row per captured launch) into the handful of numbers DESIGN.md / bench.py cite."""
 import csv, subprocess, sys, io, json
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, units, vals = rows[0], rows[1], rows[2]
-d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+hdr, units = rows[0], rows[1]
 keys = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__cluster_dim_x", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors_srcunit_tex_op_read.sum",
@@ -16,8 +15,12 @@ keys = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
         "smsp__pcsamp_warps_issue_stalled_membar", "smsp__pcsamp_warps_issue_stalled_wait", "smsp__pcsamp_warps_issue_stalled_selected",
         "smsp__pcsamp_warps_issue_stalled_short_scoreboard", "smsp__pcsamp_warps_issue_stalled_branch_resolving",
         "sm__cycles_elapsed.max", "smsp__inst_executed.sum"]
-out = {}
-for k in keys:
-    if k in d:
-        out[k] = f"{d[k][0]} {d[k][1]}".strip()
-print(json.dumps(out, indent=1))
+res = []
+for vals in rows[2:]:
+    d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+    out = {}
+    for k in keys:
+        if k in d:
+            out[k] = f"{d[k][0]} {d[k][1]}".strip()
+    res.append(out)
+print(json.dumps(res[0] if len(res) == 1 else res, indent=1))
