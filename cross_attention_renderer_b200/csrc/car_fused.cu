@@ -246,15 +246,19 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
     // loops, so the issue path is a handful of instructions per tcgen05.mma.
     if (leader) {
       const uint32_t idesc1 = make_idesc_bf16(128, N1CH), idesc3 = make_idesc_bf16(128, N3CH);
-      uint32_t bq = 0, xq = 0, hq = 0, av = 0, rq = 0;
+      uint32_t av = 0, rq = 0;
+      // ring positions as (stage, phase) counters: the ring depths are run-time values and an integer
+      // division per stage is a visible part of the single issuing thread's fixed cost
+      int sb = 0, sx = 0, sh = 0;
+      uint32_t pb = 0, px = 0, ph = 0;
+      const int nbr = p.nb;
       for (int itn = 0; itn < niter; ++itn, ++rq) {
         for (int v = 0; v < 2; ++v, ++av) {
           timed_wait(a1_empty, (av & 1) ^ 1, st, 0);                         // acc1 drained
           tc_fence_after();
-          for (int kb = 0; kb < K1_STAGES; ++kb, ++bq, ++xq) {
-            const int sb = bq % p.nb, sx = xq % NX;
-            timed_wait(&x_full[sx], (xq / NX) & 1, st, 1);
-            timed_wait(&b_full[sb], (bq / p.nb) & 1, st, 2);
+          for (int kb = 0; kb < K1_STAGES; ++kb) {
+            timed_wait(&x_full[sx], px, st, 1);
+            timed_wait(&b_full[sb], pb, st, 2);
             tc_fence_after();
             if (elect_one()) {
               const uint64_t da = make_desc<64>(smem_u32(xs + (size_t)sx * C::A_STAGE));
@@ -280,12 +284,13 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
               if (kb == K1_STAGES - 1) umma_commit_pair(a1_full, pair_mask);
             }
             __syncwarp();
+            if (++sb == nbr) { sb = 0; pb ^= 1; }
+            if (++sx == NX) { sx = 0; px ^= 1; }
           }
           if (v == 0) { timed_wait(a3_empty, (rq & 1) ^ 1, st, 3); tc_fence_after(); }
-          for (int q = 0; q < K3_STAGES; ++q, ++bq, ++hq) {
-            const int sb = bq % p.nb, sh = hq % NH;
-            timed_wait(&h_full[sh], (hq / NH) & 1, st, 4);
-            timed_wait(&b_full[sb], (bq / p.nb) & 1, st, 5);
+          for (int q = 0; q < K3_STAGES; ++q) {
+            timed_wait(&h_full[sh], ph, st, 4);
+            timed_wait(&b_full[sb], pb, st, 5);
             tc_fence_after();
             if (elect_one()) {
               const uint64_t da = make_desc<64>(smem_u32(hs + (size_t)sh * C::A_STAGE));
@@ -310,6 +315,8 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
               if (v == 1 && q == K3_STAGES - 1) umma_commit_pair(a3_full, pair_mask);
             }
             __syncwarp();
+            if (++sb == nbr) { sb = 0; pb ^= 1; }
+            if (++sh == NH) { sh = 0; ph ^= 1; }
           }
         }
       }
