@@ -175,9 +175,14 @@ __device__ __forceinline__ float nan_to_num0(float x) {   // torch.nan_to_num(x,
 
 __global__ void k_sample_geometry(car_render_args a, int g0, int g1,
                                   const RaySeg *__restrict__ seg, float *__restrict__ geom) {
+  // The 128-byte records of a block are contiguous in `geom`: they are assembled in shared memory
+  // (row stride 33 floats: conflict-free for both access patterns) and written out with coalesced
+  // 16-byte stores; 32 scalar stores per thread at a 128-byte lane stride made the kernel LSU-bound.
+  __shared__ float srec[128][33];
   long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   long n = (long)(g1 - g0) * 2 * a.P;
-  if (idx >= n) return;
+  const bool live = idx < n;
+  if (!live) idx = n - 1;                                   // compute a valid sample, store nothing
   int k = (int)(idx % a.P);
   int rj = (int)(idx / a.P);
   int j = rj & 1;
@@ -188,7 +193,7 @@ __global__ void k_sample_geometry(car_render_args a, int g0, int g1,
   float gx = sg.sx + (sg.ex - sg.sx) * iv;
   float gy = sg.sy + (sg.ey - sg.sy) * iv;
   float *pv = a.pixel_val + (((size_t)(s * 2 + j) * a.R + r) * a.P + k) * 2;
-  pv[0] = gx; pv[1] = gy;
+  if (live) *reinterpret_cast<float2 *>(pv) = make_float2(gx, gy);
 
   const float *co = a.coords + ((size_t)(s * 2 + j) * a.R + r) * 9;
   V3 d = {co[0], co[1], co[2]}, m = {co[3], co[4], co[5]}, o = {co[6], co[7], co[8]};
@@ -229,7 +234,7 @@ __global__ void k_sample_geometry(car_render_args a, int g0, int g1,
   float gxc = (xp / (float)(a.W - 1)) * 2.0f - 1.0f;
   float gyc = (yp / (float)(a.H - 1)) * 2.0f - 1.0f;
 
-  float *G = geom + (size_t)idx * CAR_GEOM_STRIDE;
+  float *G = srec[threadIdx.x];
   G[G_GX] = gx; G[G_GY] = gy; G[G_GXC] = gxc; G[G_GYC] = gyc;
   G[G_T0 + 0] = tanhf(nan_to_num0(pv0.x) / 5.0f);
   G[G_T0 + 1] = tanhf(nan_to_num0(pv0.y) / 5.0f);
@@ -255,6 +260,15 @@ __global__ void k_sample_geometry(car_render_args a, int g0, int g1,
   G[G_PTC + 1] = fminf(fmaxf(pt.y, -100.0f), 100.0f);
   G[G_PTC + 2] = fminf(fmaxf(pt.z, -100.0f), 100.0f);
   G[13] = 0.f; G[14] = 0.f; G[15] = 0.f;
+  __syncthreads();
+  const long rec0 = (long)blockIdx.x * blockDim.x;          // first record of this block
+  float4 *out = reinterpret_cast<float4 *>(geom + (size_t)rec0 * CAR_GEOM_STRIDE);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int i4 = threadIdx.x + q * 128;                   // float4 index within the block's 16 KB
+    const int rec = i4 >> 3, e = (i4 & 7) * 4;
+    if (rec0 + rec < n) out[i4] = make_float4(srec[rec][e], srec[rec][e + 1], srec[rec][e + 2], srec[rec][e + 3]);
+  }
 }
 
 }  // namespace
