@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""Evaluation driver with the reference's entry point and flags
+(``experiment_scripts/eval_realestate10k.py``):
+
+    python experiment_scripts/eval_realestate10k.py --experiment_name vis --batch_size 1 --gpus 1 \
+        --views 2 --checkpoint_path model.pth --synthetic 8
+
+Per scene: ``get_z`` once, then the whole 256x256 target in ONE ``forward`` call — the reference
+splits it into 9 ray chunks to bound activation memory (eval_realestate10k.py:144-159); here the
+chunking happens inside the library.  With ``--gpus N`` the rays of each scene are sharded across
+the ranks and the tiles all-gathered (the reference's ranks each render everything).  Prints the
+reference's ``elapsed`` and ``mse, psnr`` lines (LPIPS / SSIM need packages that are not present
+here and are skipped).
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import _common as C                                                   # noqa: E402
+
+
+def multigpu_train(gpu, opt):
+    dev = C.init_distributed(gpu, opt.gpus, opt.master_port)
+    model = C.build_model(opt, dev)
+    if opt.checkpoint_path is not None:
+        C.load_checkpoint(model, opt.checkpoint_path)
+    model = model.eval()
+    model.pixel_val_to_cpu = False
+    if not opt.synthetic:
+        raise RuntimeError("RealEstate10k frames are not available in this environment: pass --synthetic N")
+    n_scenes = opt.synthetic if not opt.max_steps else min(opt.synthetic, opt.max_steps)
+    H = opt.sidelength
+    mses, psnrs = [], []
+    with torch.no_grad():
+        for val_i in range(n_scenes):
+            model_input, gt = C.synthetic_scene_batch(1, H, 10_000 + val_i, device=dev)
+            z = model.get_z(model_input)
+            torch.cuda.synchronize()
+            start = time.time()
+            if opt.gpus > 1:
+                out = C.sharding.render_sharded(model, model_input, z)
+            else:
+                out = model(model_input, z=z, val=True)
+            torch.cuda.synchronize()
+            if gpu == 0:
+                print("elapsed: ", time.time() - start)
+            rgb = out["rgb"].view(H, H, 3)
+            valid_mask = out["valid_mask"].view(H, H, 1)
+            target = gt["rgb"].view(H, H, 3)
+            mse, psnr = C.psnr_masked(rgb, target, valid_mask)
+            mses.append(mse)
+            psnrs.append(psnr)
+            if gpu == 0:
+                print("mse, psnr", np.mean(mses), np.mean(psnrs), flush=True)
+    if opt.gpus > 1:
+        torch.distributed.destroy_process_group()
+    return float(np.mean(psnrs))
+
+
+def main(argv=None):
+    opt = C.base_parser(__doc__).parse_args(argv)
+    C.spawn(multigpu_train, opt)
+
+
+if __name__ == "__main__":
+    main()

@@ -167,6 +167,26 @@ def test_outputs_vs_oracle(staged, precision):
     assert set(out) >= {"rgb", "valid_mask", "depth_ray", "at_wt", "at_wts", "at_wt_max", "pixel_val", "coords"}
 
 
+PSNR_DELTA_DB = 0.01              # north_star: PSNR within 0.01 dB of the reference
+
+
+@pytest.mark.parametrize("precision", ["fp32_simt", "fp32"])
+def test_psnr_vs_target_within_hundredth_db(staged, precision):
+    """PSNR against a fixed synthetic target image (eval_realestate10k.py:74-75,181): the CUDA
+    render and the oracle render must score within 0.01 dB of each other."""
+    b, H, P, inp, z, sd, cams, interval, ref = staged
+    model = make_model(sd, P, H, precision=precision)
+    out = run_cuda(model, inp, z, cams=cams, interval=interval)
+    g = torch.Generator().manual_seed(5)
+    # a target at a realistic distance from the render (PSNR ~ 20-30 dB), so that the comparison is
+    # not dominated by a near-zero MSE
+    target = (ref["rgb"] + 0.1 * torch.randn(ref["rgb"].shape, generator=g)).clamp(-1.5, 1.5)
+    p_ref = orc.psnr(ref["rgb"], target)
+    p_new = orc.psnr(cpu(out["rgb"]), target)
+    assert 10.0 < p_ref < 40.0
+    assert abs(p_new - p_ref) <= PSNR_DELTA_DB, (p_new, p_ref)
+
+
 # ---------------------------------------------------------------------------------------
 # golden fixtures from the unmodified reference (full forward incl. torch pose algebra on GPU)
 # ---------------------------------------------------------------------------------------
