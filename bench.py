@@ -58,7 +58,7 @@ class ClockSampler:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=f, stderr=subprocess.DEVNULL)
+                                          "-lms", os.environ.get("CAR_CLOCK_SAMPLE_MS", "200"), "-i", str(self.index)], stdout=f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -240,7 +240,7 @@ def main():
         step_resident()
     sync_all()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("CAR_NO_CLOCK_SAMPLER"):
         sampler.start()
     nst = len(_lib.STAGES)
     import ctypes as C
@@ -249,12 +249,15 @@ def main():
         lib.car_profile_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    step_evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev0.record()
-    for _ in range(args.steps):
+    for i_ in range(args.steps):
         out = step_resident()
+        step_evs[i_].record()
     ev1.record()
     sync_all()
     ms_total = ev0.elapsed_time(ev1)
+    step_ms = [round(([ev0] + step_evs)[i_].elapsed_time(step_evs[i_]), 2) for i_ in range(args.steps)]
     if not args.no_stage_profile:
         lib.car_profile_end(ms_arr, ln_arr, nst)
     clocks = sampler.stop() if rank == 0 else None
@@ -420,7 +423,7 @@ def main():
                    "parallelism": f"ray/scene sharding x{world}, all_gather of tiles",
                    "l2": "inputs (feature maps %.0f MB per GPU) exceed the 126 MB L2" % (sum(t_.numel() * 4 for t_ in z_h) / 1e6),
                    "repacked_every_step": True, "extra_warmup_steps": extra_warm},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+        "step_ms": step_ms, "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
         "roofline": roofline, "roofline_all": roof, "stage_share": share, "stage_ms_per_step":
             {k: round(v / args.steps, 3) for k, v in stage_ms.items() if v > 0},
         "cpu_baseline": cpu_base, "parity": parity,

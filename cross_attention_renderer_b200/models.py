@@ -181,13 +181,16 @@ class CrossAttentionRenderer(nn.Module):
 
         f32 = lambda t: t.to(device=dev, dtype=torch.float32)
         Cm, q = f32(context["cam2world"]), f32(query["cam2world"])
-        Cinv = torch.inverse(Cm)                                        # models.py:207-208
+        # torch.inverse == linalg.inv_ex + a host-side check of `info` (a device sync per call, so the host
+        # could never run ahead of the GPU); the same factorisation without the check keeps the call async
+        inv = lambda m_: torch.linalg.inv_ex(m_, check_errors=False)[0]
+        Cinv = inv(Cm)                                                  # models.py:207-208
         cams = {
             "Q": torch.matmul(Cinv, q).contiguous(),
             "Cself": torch.matmul(Cinv, Cm).contiguous(),
-            "Rel": torch.stack([torch.matmul(torch.inverse(Cm[:, k:k + 1]), Cm) for k in range(2)],
+            "Rel": torch.stack([torch.matmul(inv(Cm[:, k:k + 1]), Cm) for k in range(2)],
                                dim=1).contiguous(),                     # models.py:285-286
-            "qinv": torch.inverse(q[:, 0]).contiguous(),                # geometry.py:404
+            "qinv": inv(q[:, 0]).contiguous(),                          # geometry.py:404
             "K": f32(context["intrinsics"]).contiguous(),
             "Kq": f32(query["intrinsics"])[:, 0].contiguous(),
         }
