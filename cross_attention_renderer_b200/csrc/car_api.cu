@@ -54,7 +54,7 @@ static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 // train: keep every activation the backward pass reads in its own buffer (fp32 SIMT path).
 Workspace carve(char *base, int precision, int P, int chunk, int use_fused, int train) {
   const bool fused = precision != CAR_PREC_FP32_SIMT && (use_fused & 1) && P % 64 == 0;
-  const bool tail = fused && (use_fused & 2) && P == 64;
+  const bool tail = fused && (use_fused & 2) && (P == 64 || P == 128);
   Workspace w;
   memset(&w, 0, sizeof(w));
   size_t off = 0;
@@ -378,7 +378,7 @@ int sample_stage_umma(const car_render_args &a, const Workspace &w, int g0, int 
     return launch_gemm_umma(ah, al, lda, m.hi, m.lo, m.K, M, m.N, m.K, split3, e, o, st);
   };
   const bool fused = (a.use_fused & 1) && a.P % 64 == 0;
-  const bool tail = fused && (a.use_fused & 2) && a.P == 64;
+  const bool tail = fused && (a.use_fused & 2) && (a.P == 64 || a.P == 128);
   if (fused && !W.kv_fold.hi) { set_error("use_fused needs weights.kv_fold"); return -11; }
   if (!tail) launch_split_rows(w.geom + G_LOCAL, CAR_GEOM_STRIDE, w.loc_hi, split3 ? w.loc_lo : nullptr, rows, 16, st);
   if (fused) {

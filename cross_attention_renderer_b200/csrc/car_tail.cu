@@ -1,4 +1,4 @@
-// Per-ray attention tail (P == 64): the small per-sample MLPs and both attention rounds in two
+// Per-ray attention tail (P == 64 or 128): the small per-sample MLPs and both attention rounds in two
 // kernels instead of five GEMM launches + two attention launches with every [rows x 128] fp32
 // intermediate round-tripping through HBM.
 //
@@ -12,7 +12,9 @@
 //     Q2 = query_repeat_embed_2(relu(query_repeat_embed[:,128:](local) + u_ray))
 //     s2 = <Q2,Q1>/16, softmax, z = sum a2*V + 2*z_sum
 //
-// One CTA = one ray at a time (UMMA M = 128 = the ray's 2x64 samples), persistent over the chunk:
+// One CTA = one ray at a time, persistent over the chunk.  A ray is TT = P / 64 tiles of 128 sample rows
+// (UMMA M = 128; TT = 1: both contexts in one tile, TT = 2: one tile per context): the MLPs and the row
+// dots run per tile, the joint softmax and the V sums once per ray over all of its tiles.
 //   warp 0  TMA: relu(key_map) tile and the weight K-blocks (ring)
 //   warp 1  MMA issuer (tcgen05 cta_group::1, N = 128), accumulators in TMEM
 //   warps 2-5: one thread per sample row: TMEM -> bias/ReLU -> bf16 hi/lo A operand of the next
@@ -31,11 +33,8 @@ int make_tmap_bf16(CUtensorMap *tm, const uint16_t *base, int rows, int K, int l
 namespace {
 using namespace ptx;
 
-// L2 prefetch of the next ray's V / Q1 (cp.async.bulk.prefetch.L2) doubled the DRAM reads of both phases
-// (ncu: 456 / 429 KB per ray against 291 / 220 KB algorithmic, L2 hit rate 13-20 %): off.
-#ifndef TAIL_PREFETCH
-#define TAIL_PREFETCH 0
-#endif
+// (An L2 prefetch of the next ray's V / Q1 with cp.async.bulk.prefetch.L2 doubled the DRAM reads of both
+// phases - ncu: 456 / 429 KB per ray against 291 / 220 KB algorithmic, L2 hit rate 13-20 % - and was removed.)
 constexpr int THREADS = 320;          // TMA, MMA, 4 row warps, 4 V-sum warps
 constexpr int NBMAX = 3;
 
@@ -89,7 +88,7 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ void rows_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 
 // PHASE 0 = A, 1 = B
-template <int SPLIT, int PHASE>
+template <int SPLIT, int PHASE, int TT>
 __global__ void __launch_bounds__(THREADS, 1)
 k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUtensorMap tm_kh_lo,
        const __grid_constant__ CUtensorMap tm_w0_hi, const __grid_constant__ CUtensorMap tm_w0_lo,   // key2 (A only)
@@ -104,9 +103,9 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
   const float *q1s = reinterpret_cast<const float *>(at0);
   uint8_t *at1 = at0 + (PHASE == 0 ? C::TILE : Q1_BYTES);     // local (first 32 B of each row) then the hidden tile
   uint8_t *bs = at1 + C::TILE;
-  float *arow = reinterpret_cast<float *>(bs + (size_t)p.nb * C::B_STAGE);   // [2][128] softmax weights
-  float *part = arow + 256;                                                    // [4][288] per-warp V sums
-  float *red = part + 4 * CAR_C_LAT;                                           // [32] scratch
+  float *arow = reinterpret_cast<float *>(bs + (size_t)p.nb * C::B_STAGE);   // [2][128 TT] softmax weights
+  float *part = arow + 256 * TT;                                                    // [4 TT][288] V sums per 32-row chunk
+  float *red = part + 4 * TT * CAR_C_LAT;                                      // [32] scratch
   float *vred = red + 32;                                                      // [32] scratch of the V warps
   float *sbias = vred + 32;                                                    // [3][128] hidden / output / key biases
   uint64_t *bars = reinterpret_cast<uint64_t *>(sbias + 3 * 128);
@@ -118,7 +117,12 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nrays = p.g1 - p.g0;
-  const int P = 64;
+  constexpr int P = 64 * TT;
+  // this CTA's work list: rays blockIdx.x, blockIdx.x + gridDim.x, ...; TT consecutive 128-row tiles per ray
+  const int my_rays = nrays > (int)blockIdx.x ? (nrays - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int ntile = my_rays * TT;
+  auto ray_of = [&](int it_) { return (int)blockIdx.x + (it_ / TT) * (int)gridDim.x; };
+  auto tile_of = [&](int it_) { return ray_of(it_) * TT + (it_ % TT); };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_w1_hi);
@@ -145,7 +149,7 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
-      uint32_t bq = 0, it = 0;
+      uint32_t bq = 0;
       auto load_w = [&](const CUtensorMap *hi, const CUtensorMap *lo, int k0) {
         const int s = bq % p.nb;
         mbar_wait(&b_empty[s], ((bq / p.nb) & 1) ^ 1);
@@ -155,27 +159,11 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
         if (SPLIT == 3) tma_load_2d(st + C::B_HALF, lo, &b_full[s], k0, 0);
         ++bq;
       };
-      for (int ray = blockIdx.x; ray < nrays; ray += gridDim.x, ++it) {
-#if TAIL_PREFETCH
-        {
-          // pull the next ray's V rows (and Q1 rows in phase B) into L2 ahead of the row threads
-          const int nx = ray + (it == 0 ? 0 : (int)gridDim.x);
-          for (int rr_ = nx; rr_ <= ray + (int)gridDim.x && rr_ < nrays; rr_ += gridDim.x) {
-            const char *vp = reinterpret_cast<const char *>(p.value + (size_t)rr_ * 128 * CAR_C_LAT);
-            for (int o = 0; o < 128 * CAR_C_LAT * 4; o += 16384)
-              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(vp + o), "r"(16384) : "memory");
-            if (PHASE == 1) {
-              const char *qp = reinterpret_cast<const char *>(p.q1 + (size_t)rr_ * 128 * 128);
-              for (int o = 0; o < 128 * 128 * 4; o += 16384)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(qp + o), "r"(16384) : "memory");
-            }
-          }
-        }
-#endif
+      for (int it = 0; it < ntile; ++it) {
         if (PHASE == 0) {
           mbar_wait(kh_empty, (it & 1) ^ 1);
           mbar_expect_tx(kh_full, (uint32_t)C::TILE);
-          const int r0 = ray * 128;
+          const int r0 = tile_of(it) * 128;
           tma_load_2d(at0, &tm_kh_hi, kh_full, 0, r0);
           tma_load_2d(at0 + C::KB_BYTES, &tm_kh_hi, kh_full, 64, r0);
           if (SPLIT == 3) {
@@ -195,7 +183,7 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     const uint32_t idesc = make_idesc_bf16(128, 128);
-    uint32_t bq = 0, it = 0, tq = 0;
+    uint32_t bq = 0, tq = 0;
     // one 64-wide K-block: `ksteps` MMAs (x3 in the split mode) of A(base a) x B(stage) into d
     auto gemm_kb = [&](uint32_t d, uint32_t a_addr, int ksteps, bool first) {
       const int s = bq % p.nb;
@@ -220,7 +208,7 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
       __syncwarp();
       ++bq;
     };
-    for (int ray = blockIdx.x; ray < nrays; ray += gridDim.x, ++it) {
+    for (int it = 0; it < ntile; ++it) {
       mbar_wait(done, (it & 1) ^ 1);                     // row threads finished reading both accumulators
       tc_fence_after();
       mbar_wait(loc_full, it & 1);
@@ -251,14 +239,14 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
     const int row = sub * 32 + lane;                     // 0..127: ctx = row >> 6, sample k = row & 63
     const uint32_t tlane = tmem_base + ((uint32_t)(sub * 32) << 16);
     const int rt = row;                                  // thread id among the 128 row threads (for column loops)
-    uint32_t it = 0, tq = 0;
+    uint32_t tq = 0;
     unsigned long long tacc[6] = {0, 0, 0, 0, 0, 0};     // 0 drain 1 score-wait 2 score 3 softmax 4 vsum 5 total
     const bool rec = p.stats && blockIdx.x == 0 && warp == 2;
     const long long tbeg = clock64();
-    // local_coords / clamp(pt) of a ray are fetched one ray ahead so their latency is off the critical path
+    // local_coords of a tile are fetched one tile ahead so their latency is off the critical path
     float4 l0, l1, l2, l3;
-    auto fetch_geom = [&](int ray_l) {
-      const float *Gp = p.geom + ((size_t)ray_l * 128 + row) * CAR_GEOM_STRIDE;
+    auto fetch_geom = [&](int tile_l) {
+      const float *Gp = p.geom + ((size_t)tile_l * 128 + row) * CAR_GEOM_STRIDE;
       l0 = __ldg(reinterpret_cast<const float4 *>(Gp + G_LOCAL)); l1 = __ldg(reinterpret_cast<const float4 *>(Gp + G_LOCAL + 4));
       l2 = __ldg(reinterpret_cast<const float4 *>(Gp + G_LOCAL + 8)); l3 = __ldg(reinterpret_cast<const float4 *>(Gp + G_LOCAL + 12));
     };
@@ -321,8 +309,8 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
     };
     // phase B: Q1 of a ray (64 KB, written by phase A) is staged into smem with per-thread 16-byte
     // cp.async copies issued one ray ahead (after the barrier that ends the previous ray's reads)
-    auto stage_q1 = [&](int ray_l) {
-      const char *src = reinterpret_cast<const char *>(p.q1 + (size_t)ray_l * 128 * 128);
+    auto stage_q1 = [&](int tile_l) {
+      const char *src = reinterpret_cast<const char *>(p.q1 + (size_t)tile_l * 128 * 128);
       const uint32_t dst = smem_u32(at0);
 #pragma unroll 8
       for (int k = 0; k < 32; ++k) {
@@ -331,18 +319,20 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    if ((int)blockIdx.x < nrays) {
-      if (PHASE == 1) stage_q1(blockIdx.x);
-      fetch_geom(blockIdx.x);
+    if (ntile > 0) {
+      if (PHASE == 1) stage_q1(tile_of(0));
+      fetch_geom(tile_of(0));
       write_loc();
-      if ((int)(blockIdx.x + gridDim.x) < nrays) fetch_geom(blockIdx.x + gridDim.x);
-      drain_hidden(blockIdx.x);
+      if (ntile > 1) fetch_geom(tile_of(1));
+      drain_hidden(ray_of(0));
     }
-    for (int ray = blockIdx.x; ray < nrays; ray += gridDim.x, ++it) {
+    float sc_prev = 0.f;                                 // TT == 2: score of this row in the ray's first tile
+    for (int it = 0; it < ntile; ++it) {
+      const int tile = tile_of(it), t = it % TT;
       // ---- scores: <K,Q1> (phase A) or <Q2,Q1> (phase B), each thread its own row ----
       float sc = 0.f;
       long long tt = rec ? clock64() : 0;
-      float *q1col = p.q1 + (size_t)ray * 128 * 128 + row;      // element (col c, this row) at q1col[c * 128]
+      float *q1col = p.q1 + (size_t)tile * 128 * 128 + row;     // element (col c, this row) at q1col[c * 128]
       if (PHASE == 0) { mbar_wait(k_full, it & 1); }
       else { asm volatile("cp.async.wait_group 0;" ::: "memory"); rows_sync(); }   // every thread's Q1 chunks landed
       mbar_wait(t_full, tq & 1); ++tq;
@@ -390,37 +380,45 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
       if (lane == 0) {
         mbar_arrive(done);                               // accumulators and at1 may be reused
       }
-      if (ray + (int)gridDim.x < nrays) {                 // next ray's K=16 operand (at1 is free: hidden GEMM retired)
+      if (it + 1 < ntile) {                               // next tile's K=16 operand (at1 is free: hidden GEMM retired)
         write_loc();
-        if (ray + 2 * (int)gridDim.x < nrays) fetch_geom(ray + 2 * gridDim.x);
+        if (it + 2 < ntile) fetch_geom(tile_of(it + 2));
       }
       if (rec) { tacc[2] += (unsigned long long)(clock64() - tt); tt = clock64(); }
       sc = sc / 16.0f;
-      // ---- joint softmax over the 128 samples of the ray ----
-      float mx = warp_max(sc);
+      if (TT == 2 && t == 0) {
+        // first tile of the ray: keep the score, hand the pipeline to the second tile
+        sc_prev = sc;
+        if (PHASE == 1) { rows_sync(); stage_q1(tile_of(it + 1)); }   // all four warps are past their Q1 reads
+        drain_hidden(ray_of(it + 1));
+        continue;
+      }
+      // ---- joint softmax over the ray's 128 TT samples (this thread: one row per tile) ----
+      float mx = warp_max(TT == 2 ? fmaxf(sc, sc_prev) : sc);
       if (lane == 0) red[sub] = mx;
       rows_sync();
-      if (PHASE == 1 && ray + (int)gridDim.x < nrays) stage_q1(ray + gridDim.x);   // all four warps are past their Q1 reads
+      if (PHASE == 1 && it + 1 < ntile) stage_q1(tile_of(it + 1));   // all four warps are past their Q1 reads
       mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-      const float e = expf(sc - mx);
-      float sm = warp_sum(e);
+      const float e = expf(sc - mx), e0 = TT == 2 ? expf(sc_prev - mx) : 0.f;
+      float sm = warp_sum(TT == 2 ? e0 + e : e);
       if (lane == 0) red[4 + sub] = sm;
       rows_sync();
       sm = (red[4] + red[5]) + (red[6] + red[7]);
       const float aw = e / sm;
       {
-        // post the weights for the V-sum warps (double-buffered: buffer it&1 was last read two rays ago)
+        // post the weights for the V-sum warps (double-buffered per ray: buffer ir&1 was last read two rays ago)
         const long long tw = rec ? clock64() : 0;
-        const uint32_t buf = it & 1;
-        mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1);
-        arow[buf * 128 + row] = aw;
+        const uint32_t ir = (uint32_t)(it / TT), buf = ir & 1;
+        mbar_wait(&a_empty[buf], ((ir >> 1) & 1) ^ 1);
+        if (TT == 2) arow[buf * 256 + row] = e0 / sm;
+        arow[buf * (128 * TT) + (TT - 1) * 128 + row] = aw;
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_full[buf]);
         if (rec) tacc[4] += (unsigned long long)(clock64() - tw);
       }
       if (rec) tacc[3] += (unsigned long long)(clock64() - tt);
-      // next ray's hidden layer: its 128x128 GEMM then runs while the V warps sum this ray
-      if (ray + (int)gridDim.x < nrays) drain_hidden(ray + gridDim.x);
+      // next tile's hidden layer: its 128x128 GEMM then runs while the V warps sum this ray
+      if (it + 1 < ntile) drain_hidden(ray_of(it + 1));
     }
     if (rec && lane == 0) {
       tacc[5] = (unsigned long long)(clock64() - tbeg);
@@ -428,82 +426,93 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
     }
   } else {
     // =========================== V-sum warps (6..9) ===========================
-    // warp vs sums rows [32 vs, 32 vs + 32) of the ray: sum_i a[i] * V[i][0..288), lanes over float4 columns
+    // per tile, warp vs sums rows [32 vs, 32 vs + 32): sum_i a[i] * V[i][0..288), lanes over float4 columns
     const int vs = warp - 6;
     const int vt = vs * 32 + lane;
     const bool rec = p.stats && blockIdx.x == 0 && vs == 0;
     unsigned long long vacc[3] = {0, 0, 0};              // 0 wait weights 1 loads+fma 2 reduce+store
     const int l2 = lane < 8 ? 64 + lane : lane;          // third float4 column only exists for lanes 0..7
     const float m2 = lane < 8 ? 1.f : 0.f;
-    uint32_t it = 0;
-    for (int ray = blockIdx.x; ray < nrays; ray += gridDim.x, ++it) {
-      const uint32_t buf = it & 1;
-      const float *V = p.value + ((size_t)ray * 128 + vs * 32) * CAR_C_LAT;
-      const float *aw = arow + buf * 128 + vs * 32;
-      float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0, acc2 = acc0;
-      float4 v0[2][4], v1[2][4], v2[2][4];
-      auto loadb = [&](int b, int s_) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 *vr = reinterpret_cast<const float4 *>(V + (size_t)(b * 4 + i) * CAR_C_LAT);
-          v0[s_][i] = __ldg(vr + lane); v1[s_][i] = __ldg(vr + 32 + lane); v2[s_][i] = __ldg(vr + l2);
-        }
-      };
-      long long tv = rec ? clock64() : 0;
-      loadb(0, 0);
-      loadb(1, 1);
-      float ptx = 0.f, pty = 0.f, ptz = 0.f;            // clamp(pt) of row vt (phase A: expected depth)
-      if (PHASE == 0) {
-        const float *Gp = p.geom + ((size_t)ray * 128 + vt) * CAR_GEOM_STRIDE + G_PTC;
-        ptx = __ldg(Gp); pty = __ldg(Gp + 1); ptz = __ldg(Gp + 2);
-      }
-      mbar_wait(&a_full[buf], (it >> 1) & 1);
-      if (rec) { vacc[0] += (unsigned long long)(clock64() - tv); tv = clock64(); }
+    for (int ir = 0; ir < my_rays; ++ir) {
+      const int ray = (int)blockIdx.x + ir * (int)gridDim.x;
+      const uint32_t buf = (uint32_t)ir & 1;
       const int g = p.g0 + ray, scene = g / p.a.R, rr = g - scene * p.a.R;
-      if (PHASE == 0) {
-        // outputs that only need the posted weights: at_wt, per-context argmax, expected 3-D point
-        const float awr = arow[buf * 128 + vt];
-        const int ctx = vt >> 6, kk = vt & 63;
-        p.a.at_wt[((size_t)(scene * 2 + ctx) * p.a.R + rr) * P + kk] = awr;
-        float bv = awr; int bi = kk;                     // first maximum: warp-level, then across the context's two warps
+      float w0 = 0.f, w1 = 0.f, w2 = 0.f;               // phase A: this warp's share of sum a * clamp(pt)
+      long long tv = rec ? clock64() : 0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      for (int t = 0; t < TT; ++t) {
+        const int tile = ray * TT + t;
+        const float *V = p.value + ((size_t)tile * 128 + vs * 32) * CAR_C_LAT;
+        const float *aw = arow + buf * (128 * TT) + t * 128 + vs * 32;
+        float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0, acc2 = acc0;
+        float4 v0[2][4], v1[2][4], v2[2][4];
+        auto loadb = [&](int b, int s_) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 *vr = reinterpret_cast<const float4 *>(V + (size_t)(b * 4 + i) * CAR_C_LAT);
+            v0[s_][i] = __ldg(vr + lane); v1[s_][i] = __ldg(vr + 32 + lane); v2[s_][i] = __ldg(vr + l2);
+          }
+        };
+        loadb(0, 0);
+        loadb(1, 1);
+        float ptx = 0.f, pty = 0.f, ptz = 0.f;          // clamp(pt) of row vt (phase A: expected depth)
+        if (PHASE == 0) {
+          const float *Gp = p.geom + ((size_t)tile * 128 + vt) * CAR_GEOM_STRIDE + G_PTC;
+          ptx = __ldg(Gp); pty = __ldg(Gp + 1); ptz = __ldg(Gp + 2);
         }
-        const float w0 = warp_sum(awr * ptx), w1 = warp_sum(awr * pty), w2 = warp_sum(awr * ptz);   // models.py:577-582
-        if (lane == 0) {
-          vred[8 + vs] = bv; reinterpret_cast<int *>(vred)[12 + vs] = bi;
-          vred[16 + vs * 3] = w0; vred[17 + vs * 3] = w1; vred[18 + vs * 3] = w2;
+        if (t == 0) {
+          mbar_wait(&a_full[buf], ((uint32_t)ir >> 1) & 1);
+          if (rec) { vacc[0] += (unsigned long long)(clock64() - tv); tv = clock64(); }
         }
+        if (PHASE == 0) {
+          // outputs that only need the posted weights: at_wt, per-context argmax, expected 3-D point
+          const float awr = aw[lane];
+          const int lr = t * 128 + vt, ctx = lr / P, kk = lr - ctx * P;   // row of the ray -> (context, sample)
+          p.a.at_wt[((size_t)(scene * 2 + ctx) * p.a.R + rr) * P + kk] = awr;
+          float bv = awr; int bi = kk;                   // first maximum of this 32-row chunk
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+          }
+          w0 += warp_sum(awr * ptx); w1 += warp_sum(awr * pty); w2 += warp_sum(awr * ptz);   // models.py:577-582
+          if (lane == 0) { vred[t * 4 + vs] = bv; reinterpret_cast<int *>(vred)[8 + t * 4 + vs] = bi; }
+        }
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          const float4 a4 = *reinterpret_cast<const float4 *>(aw + b * 4);
+          const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float a = av[i], a2 = a * m2;
+            const float4 x0 = v0[b & 1][i], x1 = v1[b & 1][i], x2 = v2[b & 1][i];
+            acc0.x = fmaf(a, x0.x, acc0.x); acc0.y = fmaf(a, x0.y, acc0.y); acc0.z = fmaf(a, x0.z, acc0.z); acc0.w = fmaf(a, x0.w, acc0.w);
+            acc1.x = fmaf(a, x1.x, acc1.x); acc1.y = fmaf(a, x1.y, acc1.y); acc1.z = fmaf(a, x1.z, acc1.z); acc1.w = fmaf(a, x1.w, acc1.w);
+            acc2.x = fmaf(a2, x2.x, acc2.x); acc2.y = fmaf(a2, x2.y, acc2.y); acc2.z = fmaf(a2, x2.z, acc2.z); acc2.w = fmaf(a2, x2.w, acc2.w);
+          }
+          if (b + 2 < 8) loadb(b + 2, b & 1);
+        }
+        float4 *pp = reinterpret_cast<float4 *>(part + (t * 4 + vs) * CAR_C_LAT);   // 32-row chunk t*4+vs of the ray
+        pp[lane] = acc0; pp[32 + lane] = acc1;
+        if (lane < 8) pp[64 + lane] = acc2;
       }
-#pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        const float4 a4 = *reinterpret_cast<const float4 *>(aw + b * 4);
-        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float a = av[i], a2 = a * m2;
-          const float4 x0 = v0[b & 1][i], x1 = v1[b & 1][i], x2 = v2[b & 1][i];
-          acc0.x = fmaf(a, x0.x, acc0.x); acc0.y = fmaf(a, x0.y, acc0.y); acc0.z = fmaf(a, x0.z, acc0.z); acc0.w = fmaf(a, x0.w, acc0.w);
-          acc1.x = fmaf(a, x1.x, acc1.x); acc1.y = fmaf(a, x1.y, acc1.y); acc1.z = fmaf(a, x1.z, acc1.z); acc1.w = fmaf(a, x1.w, acc1.w);
-          acc2.x = fmaf(a2, x2.x, acc2.x); acc2.y = fmaf(a2, x2.y, acc2.y); acc2.z = fmaf(a2, x2.z, acc2.z); acc2.w = fmaf(a2, x2.w, acc2.w);
-        }
-        if (b + 2 < 8) loadb(b + 2, b & 1);
-      }
+      if (PHASE == 0 && lane == 0) { vred[16 + vs * 3] = w0; vred[17 + vs * 3] = w1; vred[18 + vs * 3] = w2; }
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_empty[buf]);        // weights of this buffer consumed
       if (rec) { vacc[1] += (unsigned long long)(clock64() - tv); tv = clock64(); }
-      float4 *pp = reinterpret_cast<float4 *>(part + vs * CAR_C_LAT);
-      pp[lane] = acc0; pp[32 + lane] = acc1;
-      if (lane < 8) pp[64 + lane] = acc2;
       asm volatile("bar.sync 3, 128;" ::: "memory");
       if (PHASE == 0 && vt < 2) {
-        const int c = vt;                                // context c = rows [64c, 64c+64) = V warps 2c, 2c+1
-        const float m0 = vred[8 + 2 * c], m1 = vred[8 + 2 * c + 1];
-        const int i0 = reinterpret_cast<int *>(vred)[12 + 2 * c], i1 = reinterpret_cast<int *>(vred)[12 + 2 * c + 1];
-        p.a.at_wt_max[(size_t)(scene * 2 + c) * p.a.R + rr] = (m1 > m0) ? i1 : i0;
+        // context c = rows [c P, (c+1) P) = chunks [2 TT c, 2 TT (c+1)) in row order: first maximum wins
+        const int c = vt;
+        float m0 = vred[2 * TT * c];
+        int i0 = reinterpret_cast<int *>(vred)[8 + 2 * TT * c];
+#pragma unroll
+        for (int q = 1; q < 2 * TT; ++q) {
+          const float m1 = vred[2 * TT * c + q];
+          if (m1 > m0) { m0 = m1; i0 = reinterpret_cast<int *>(vred)[8 + 2 * TT * c + q]; }
+        }
+        p.a.at_wt_max[(size_t)(scene * 2 + c) * p.a.R + rr] = i0;
       }
       if (PHASE == 0 && vt == 2) {
         const float x = (vred[16] + vred[19]) + (vred[22] + vred[25]);
@@ -514,8 +523,14 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
         p.a.depth_ray[(size_t)scene * p.a.R + rr] = fminf(fmaxf(zc, 0.f), 10.f);
       }
       for (int c = vt; c < CAR_C_LAT; c += 128) {
-        const float z0 = part[0 * CAR_C_LAT + c] + part[1 * CAR_C_LAT + c];      // context 0 = rows 0..63
-        const float z1 = part[2 * CAR_C_LAT + c] + part[3 * CAR_C_LAT + c];      // context 1
+        float z0, z1;                                    // per-context sums: chunks [0, 2 TT) and [2 TT, 4 TT)
+        if (TT == 1) {
+          z0 = part[0 * CAR_C_LAT + c] + part[1 * CAR_C_LAT + c];
+          z1 = part[2 * CAR_C_LAT + c] + part[3 * CAR_C_LAT + c];
+        } else {
+          z0 = (part[0 * CAR_C_LAT + c] + part[1 * CAR_C_LAT + c]) + (part[2 * CAR_C_LAT + c] + part[3 * CAR_C_LAT + c]);
+          z1 = (part[4 * CAR_C_LAT + c] + part[5 * CAR_C_LAT + c]) + (part[6 * CAR_C_LAT + c] + part[7 * CAR_C_LAT + c]);
+        }
         if (PHASE == 0) {
           p.zsum[(size_t)ray * CAR_C_LAT + c] = z0 + z1;                         // models.py:537-540
         } else {
@@ -523,7 +538,7 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
           p.zfin[(size_t)ray * CAR_C_LAT + c] = (z0 + zs) + (z1 + zs);           // models.py:561-564
         }
       }
-      asm volatile("bar.sync 3, 128;" ::: "memory");    // part[] reused by the next ray
+      asm volatile("bar.sync 3, 128;" ::: "memory");    // part[], vred[] reused by the next ray
       if (rec) vacc[2] += (unsigned long long)(clock64() - tv);
     }
     if (rec && lane == 0)
@@ -546,7 +561,8 @@ int launch_tail(const car_render_args &a, int phase, int g0, int g1, const float
                 float *zfin, cudaStream_t st) {
   const int split3 = a.precision == CAR_PREC_FP32_3XBF16;
   const car_weights &W = a.weights;
-  if (a.P != 64) { set_error("tail kernel needs P == 64"); return -30; }
+  if (a.P != 64 && a.P != 128) { set_error("tail kernel needs P == 64 or 128"); return -30; }
+  const int TT = a.P / 64;
   const int nrays = g1 - g0;
   const car_mat &w0 = W.key2, &w1 = phase == 0 ? W.qry1 : W.rep1_loc, &w2 = phase == 0 ? W.qry2 : W.rep2;
   CUtensorMap tk_h, tk_l, t0h, t0l, t1h, t1l, t2h, t2l;
@@ -556,7 +572,7 @@ int launch_tail(const car_render_args &a, int phase, int g0, int g1, const float
     if (split3) { if ((rc = make_tmap_bf16(tl, lo, rows, K, K, 128, 64))) return rc; } else *tl = *th;
     return 0;
   };
-  if (phase == 0) { if (mk(&tk_h, &tk_l, kh_hi, kh_lo, nrays * 128, 128)) return rc; }
+  if (phase == 0) { if (mk(&tk_h, &tk_l, kh_hi, kh_lo, nrays * 128 * TT, 128)) return rc; }
   if (mk(&t0h, &t0l, w0.hi, w0.lo, 128, 128)) return rc;
   if (mk(&t1h, &t1l, w1.hi, w1.lo, 128, 16)) return rc;
   if (mk(&t2h, &t2l, w2.hi, w2.lo, 128, 128)) return rc;
@@ -568,7 +584,7 @@ int launch_tail(const car_render_args &a, int phase, int g0, int g1, const float
   p.bias_k2 = W.key2.bias; p.bias_q1 = W.qry1.bias; p.bias_q2 = W.qry2.bias; p.bias_r2 = W.rep2.bias;
   const int ops = split3 ? 2 : 1;
   const size_t tile = 2 * 128 * 128 * ops, bstage = 128 * 128 * ops;
-  const size_t fixed = (phase == 0 ? 2 * tile : tile + 128 * 128 * 4) + (256 + 4 * CAR_C_LAT + 64 + 3 * 128) * 4 + (12 + 2 * NBMAX) * 8 + 16 + 512;
+  const size_t fixed = (phase == 0 ? 2 * tile : tile + 128 * 128 * 4) + (256 * TT + 4 * TT * CAR_C_LAT + 64 + 3 * 128) * 4 + (12 + 2 * NBMAX) * 8 + 16 + 512;
   int nb = (int)((227 * 1024 - fixed) / bstage);
   if (nb > NBMAX) nb = NBMAX;
   if (nb < 2) { set_error("tail: not enough shared memory"); return -31; }
@@ -579,14 +595,16 @@ int launch_tail(const car_render_args &a, int phase, int g0, int g1, const float
   const int grid = nrays < sms ? nrays : sms;
   cudaError_t e = cudaSuccess;
   prof_pre(CAR_ST_ATTENTION, st);
-#define CAR_TAIL(S, PH)                                                                              \
-  do {                                                                                               \
-    e = cudaFuncSetAttribute(k_tail<S, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-    if (e == cudaSuccess)                                                                            \
-      k_tail<S, PH><<<grid, THREADS, smem, st>>>(tk_h, tk_l, t0h, t0l, t1h, t1l, t2h, t2l, p);        \
+#define CAR_TAIL(S, PH, T)                                                                              \
+  do {                                                                                                  \
+    e = cudaFuncSetAttribute(k_tail<S, PH, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+    if (e == cudaSuccess)                                                                               \
+      k_tail<S, PH, T><<<grid, THREADS, smem, st>>>(tk_h, tk_l, t0h, t0l, t1h, t1l, t2h, t2l, p);        \
   } while (0)
-  if (split3) { if (phase == 0) CAR_TAIL(3, 0); else CAR_TAIL(3, 1); }
-  else { if (phase == 0) CAR_TAIL(1, 0); else CAR_TAIL(1, 1); }
+#define CAR_TAIL_T(S, PH) do { if (TT == 1) CAR_TAIL(S, PH, 1); else CAR_TAIL(S, PH, 2); } while (0)
+  if (split3) { if (phase == 0) CAR_TAIL_T(3, 0); else CAR_TAIL_T(3, 1); }
+  else { if (phase == 0) CAR_TAIL_T(1, 0); else CAR_TAIL_T(1, 1); }
+#undef CAR_TAIL_T
 #undef CAR_TAIL
   prof_post(st);
   if (e != cudaSuccess) { set_error("tail: %s", cudaGetErrorString(e)); return (int)e; }

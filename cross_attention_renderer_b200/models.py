@@ -103,7 +103,7 @@ class CrossAttentionRenderer(nn.Module):
         self.feature_dtype = None            # None: fp32 for fp32*, bf16 for bf16
         self.pixel_val_to_cpu = True         # reference returns pixel_val on the host (models.py:570)
         self.chunk_rays = None
-        # bit 0: fused gather+encode kernel, bit 1: fused attention tail (P == 64 only)
+        # bit 0: fused gather+encode kernel, bit 1: fused attention tail (P == 64 or 128)
         self.use_fused = int(os.environ.get("CAR_FUSED", "3"))
         self._wcache = None
         self._fcache = None

@@ -144,7 +144,7 @@ typedef struct car_render_args {
   car_debug debug;                /* all-NULL in production                                  */
   void *stream;                   /* cudaStream_t                                            */
   int32_t use_fused;              /* bit 0: fused gather+encode kernel, bit 1: fused per-ray
-                                     attention tail (both need P == 64; else the unfused path).
+                                     attention tail (encode: P % 64 == 0; tail: P == 64 or 128; else the unfused path).
                                      debug.interp needs bit 0 clear, debug.key/q2 bit 1 clear.   */
   int32_t train;                  /* 1: training-mode forward (reference training.py:92): the whole
                                      ray range is processed as one chunk on the unfused fp32 path and

@@ -154,5 +154,5 @@ def test_training_step_reduces_loss():
         loss = (out["rgb"] - target).abs().mean()
         loss.backward()
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     assert losses[-1] < losses[0], losses

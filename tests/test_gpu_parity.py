@@ -346,11 +346,13 @@ def test_fused_encode_matches_unfused(precision, feat):
                               atol=2e-4 * float(ref["_I"]["value"].abs().max()))
 
 
+@pytest.mark.parametrize("P", [64, 128])
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_fused_tail_matches(precision):
-    """Per-ray tail kernels (K/Q1/Q2 MLPs + both attention rounds) against the separate GEMM +
-    attention kernels, and against the oracle for the fp32 precision."""
-    b, H, Ht, P = 2, 64, 24, 64
+def test_fused_tail_matches(precision, P):
+    """Per-ray tail kernels (K/Q1/Q2 MLPs + both attention rounds; P = 128: two 128-row tiles per
+    ray, BASELINE config 4) against the separate GEMM + attention kernels, and against the oracle
+    for the fp32 precision."""
+    b, H, Ht = 2, 64, 24
     inp = synthetic.make_inputs(b, H, Ht, seed=44, mode="mixed")
     z = synthetic.make_features(b, H, seed=44)
     sd = synthetic.make_state_dict(seed=44, peaky=True)
@@ -385,8 +387,8 @@ def test_fused_tail_matches(precision):
 
 @pytest.mark.parametrize("P", [128, 192])
 def test_fused_encode_long_lines(P):
-    """P = 128 (BASELINE config 4) / 192: the fused encode kernel takes 64-sample groups, the
-    attention tail runs unfused."""
+    """P = 128 (BASELINE config 4) / 192: the fused encode kernel takes 64-sample groups; the
+    attention tail is fused for P = 128 and runs unfused for P = 192."""
     b, H, Ht = 1, 64, 10
     inp = synthetic.make_inputs(b, H, Ht, seed=55, mode="default")
     z = synthetic.make_features(b, H, seed=55)
