@@ -404,3 +404,41 @@ def test_fused_encode_long_lines(P):
         assert rel_err(cpu(outs[mode]["rgb"]), ref["rgb"]) < 1e-4, mode
         assert torch.equal(outs[mode]["pixel_val"], ref["pixel_val"])
     assert rel_err(cpu(outs[3]["rgb"]), cpu(outs[0]["rgb"])) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------
+# edge cases: single ray, ragged ray counts smaller than the grid, empty shard
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32_simt", "fp32"])
+@pytest.mark.parametrize("rays", [1, 3, 149])
+def test_small_and_ragged_ray_counts(precision, rays):
+    """Fewer rays than CTAs / than one MMA tile, odd counts: same results as the oracle."""
+    b, H, P = 2, 64, 64
+    inp = synthetic.make_inputs(b, H, H, seed=66, mode="mixed", rays=rays)
+    z = synthetic.make_features(b, H, seed=66)
+    sd = synthetic.make_state_dict(seed=66)
+    cams = orc.prepare_cameras(inp)
+    interval = torch.linspace(0, 1, P)
+    with torch.no_grad():
+        ref = orc.render(sd, inp, z, H, H, P, interval=interval, cams=cams)
+    out = run_cuda(make_model(sd, P, H, precision=precision), inp, z, cams=cams, interval=interval)
+    assert out["rgb"].shape == (b, 1, rays, 3) and out["at_wt"].shape == (b * 2, rays, P)
+    assert rel_err(cpu(out["rgb"]), ref["rgb"]) < 1e-4
+    assert torch.equal(cpu(out["pixel_val"]), ref["pixel_val"])
+    assert torch.equal(cpu(out["valid_mask"]), ref["valid_mask"])
+
+
+def test_empty_shard_is_a_no_op():
+    """A rank whose ray range is empty (more ranks than rays) launches nothing and returns zeros."""
+    b, H, P = 1, 32, 64
+    inp = synthetic.make_inputs(b, H, H, seed=67, rays=5)
+    z = synthetic.make_features(b, H, seed=67)
+    sd = synthetic.make_state_dict(seed=67)
+    m = make_model(sd, P, H, precision="fp32")
+    out = run_cuda(m, inp, z, ray_range=(3, 3))
+    assert m.last_launch_count == 0
+    assert float(out["rgb"].abs().sum()) == 0.0
+    full = run_cuda(m, inp, z)
+    part = run_cuda(m, inp, z, ray_range=(2, 5))
+    assert torch.equal(part["rgb"][:, :, 2:5], full["rgb"][:, :, 2:5])
+    assert float(part["rgb"][:, :, :2].abs().sum()) == 0.0
