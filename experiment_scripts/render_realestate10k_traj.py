@@ -61,7 +61,7 @@ def render(gpu, opt):
             model_input, _ = C.synthetic_scene_batch(1, H, 20_000 + scene, device=dev)
             z = model.get_z(model_input)                              # render_realestate10k_traj.py:97
             poses = trajectory(model_input["context"]["cam2world"][0], opt.frames)
-            frames = []
+            frames, t_frame = [], []
             torch.cuda.synchronize()
             t0 = time.time()
             for i in range(opt.frames):
@@ -71,12 +71,18 @@ def render(gpu, opt):
                 else:
                     out = model(model_input, z=z)
                 frames.append(out["rgb"].view(H, H, 3))
+                if opt.frame_times:
+                    torch.cuda.synchronize()
+                    t_frame.append(time.time())
             torch.cuda.synchronize()
             dt = time.time() - t0
             rps = opt.frames * H * H / dt
             results.append(rps)
             if gpu == 0:
                 print(f"scene {scene}: {opt.frames} frames in {dt:.3f} s = {rps:,.0f} rays/s", flush=True)
+                if opt.frame_times:
+                    ms = [round(1e3 * (b_ - a_), 1) for a_, b_ in zip([t0] + t_frame[:-1], t_frame)]
+                    print("  ms per frame:", ms, flush=True)
                 scene_dir = os.path.join(out_root, f"scene_{scene:04d}")
                 os.makedirs(scene_dir, exist_ok=True)
                 for i, fr in enumerate(frames):
@@ -93,6 +99,7 @@ def render(gpu, opt):
 def main(argv=None):
     p = C.base_parser(__doc__)
     p.add_argument("--frames", type=int, default=16)
+    p.add_argument("--frame_times", action="store_true", help="synchronise after every frame and print its latency")
     opt = p.parse_args(argv)
     C.spawn(render, opt)
 
