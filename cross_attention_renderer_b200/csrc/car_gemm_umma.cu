@@ -241,7 +241,17 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
       const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * acc_stride);
       const float *rb = (p.row_bias && row < p.M) ? p.row_bias + (size_t)(row / p.rows_per_group) * p.N : nullptr;
       // 32 accumulator columns per step: one 128-byte line of fp32 (or 64 B of bf16) per lane
-      auto emit = [&](const uint32_t *r, int c0, int cnt) {
+      // The residual / accumulate source of a 32-column block (fp32, one 128-byte line per lane) is fetched
+      // in one batch BEFORE the block's math (and before the TMEM wait of the caller): consumed load by
+      // load it cost one global round trip per 8 columns, 16 per tile, and dominated the small GEMMs.
+      auto fetch_add = [&](float4 (&av)[8], int c0, int cnt) {
+        if (!p.add_src || row >= p.M) return;
+        const float4 *src = reinterpret_cast<const float4 *>(p.add_src + (size_t)row * p.ldc + n0 + c0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i * 4 < cnt) av[i] = src[i];
+      };
+      auto emit = [&](const uint32_t *r, const float4 (&av)[8], int c0, int cnt) {
         if (row >= p.M) return;
 #pragma unroll
         for (int i0 = 0; i0 < 32; i0 += 8) {
@@ -250,15 +260,19 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
           const size_t o = (size_t)row * p.ldc + n;
           float v[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float x = __uint_as_float(r[i0 + i]);
-            if (p.bias) x += __ldg(p.bias + n + i);
-            if (rb) x += __ldg(rb + n + i);
-            v[i] = x;
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i0 + i]);
+          if (p.bias) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(p.bias + n)), b1 = __ldg(reinterpret_cast<const float4 *>(p.bias + n + 4));
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          }
+          if (rb) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(rb + n)), b1 = __ldg(reinterpret_cast<const float4 *>(rb + n + 4));
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
           }
           if (p.add_src) {
-            const float4 a0 = *reinterpret_cast<const float4 *>(p.add_src + o);
-            const float4 a1 = *reinterpret_cast<const float4 *>(p.add_src + o + 4);
+            const float4 a0 = av[i0 / 4], a1 = av[i0 / 4 + 1];
             v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
             v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
           }
@@ -287,23 +301,28 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
       };
       {
         uint32_t r0[32], r1[32];
+        float4 a0[8], a1[8];
         const int n32 = p.BN / 32;
-        if (n32 > 0) tmem_ld32(taddr, r0);
+        if (n32 > 0) { tmem_ld32(taddr, r0); fetch_add(a0, 0, 32); }
         for (int j = 0; j < n32; j += 2) {
           tmem_ld_wait();
-          if (j + 1 < n32) tmem_ld32(taddr + (uint32_t)((j + 1) * 32), r1);
-          emit(r0, j * 32, 32);
+          if (j + 1 < n32) { tmem_ld32(taddr + (uint32_t)((j + 1) * 32), r1); fetch_add(a1, (j + 1) * 32, 32); }
+          emit(r0, a0, j * 32, 32);
           if (j + 1 < n32) {
             tmem_ld_wait();
-            if (j + 2 < n32) tmem_ld32(taddr + (uint32_t)((j + 2) * 32), r0);
-            emit(r1, (j + 1) * 32, 32);
+            if (j + 2 < n32) { tmem_ld32(taddr + (uint32_t)((j + 2) * 32), r0); fetch_add(a0, (j + 2) * 32, 32); }
+            emit(r1, a1, (j + 1) * 32, 32);
           }
         }
         if (p.BN & 16) {
           uint32_t rt[16];
           tmem_ld16(taddr + (uint32_t)(n32 * 32), rt);
+          fetch_add(a0, n32 * 32, 16);
           tmem_ld_wait();
-          emit(rt, n32 * 32, 16);
+          uint32_t rt32[32];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) rt32[i] = rt[i];
+          emit(rt32, a0, n32 * 32, 16);
         }
       }
       tcgen05_fence_before();
