@@ -7,7 +7,8 @@ from cross_attention_renderer_b200.models import CrossAttentionRenderer
 prec = sys.argv[1] if len(sys.argv) > 1 else "fp32"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 quiet = len(sys.argv) > 3
-b, H, P = 1, 256, 64
+b, H = 1, 256
+P = int(os.environ.get("CAR_DIAG_P", "64"))
 inp = synthetic.to_device(synthetic.make_inputs(b, H, H, seed=1), "cuda")
 z = [t.cuda() for t in synthetic.make_features(b, H, seed=1)]
 m = CrossAttentionRenderer(n_view=2, npoints=P, precision=prec).cuda()
