@@ -21,8 +21,11 @@ D_IN_PHI_PER_VIEW = 9    # plucker(6) + origin(3), models.py:144,597
 
 def renderer_param_shapes(n_view=2, num_hidden_units_phi=128):
     """Ordered {name: shape} of every non-encoder parameter (models.py:96-145)."""
-    if n_view != 2:
-        raise NotImplementedError("hot path covers n_view=2 (SURVEY §8)")
+    if n_view not in (1, 2, 3):
+        raise NotImplementedError("the reference defines n_view in {1, 2, 3}")
+    # n_view > 1: the per-sample encoder halves the latent (models.py:100-104); n_view == 1 keeps the
+    # 576 channels and merges the 6 point channels with update_val_merge (models.py:107-108)
+    LATENT = LATENT_IN // 2 if n_view > 1 else LATENT_IN
     h = HIDDEN
     hp = num_hidden_units_phi
     s = OrderedDict()
@@ -32,9 +35,12 @@ def renderer_param_shapes(n_view=2, num_hidden_units_phi=128):
         s[name + ".bias"] = (cout,)
 
     conv2d("conv_map", 3, 64, 7)                                  # models.py:96
-    conv2d("query_encode_latent", LATENT_IN + 3, LATENT_IN)       # :102
-    conv2d("query_encode_latent_2", LATENT_IN, LATENT)            # :103
-    conv2d("update_val_merge", LATENT * 2 + 6, LATENT)            # :105
+    if n_view > 1:
+        conv2d("query_encode_latent", LATENT_IN + 3, LATENT_IN)   # :102
+        conv2d("query_encode_latent_2", LATENT_IN, LATENT)        # :103
+        conv2d("update_val_merge", LATENT * 2 + 6, LATENT)        # :105
+    else:
+        conv2d("update_val_merge", LATENT + 6, LATENT)            # :108
     conv2d("latent_value", LATENT * n_view, LATENT)               # :117
     conv2d("key_map", LATENT * n_view, h)                         # :118
     conv2d("key_map_2", h, h)                                     # :119

@@ -44,8 +44,9 @@ def make_uv(Ht, Wt):
     return torch.stack([xs, ys], dim=-1).reshape(-1, 2)
 
 
-def make_inputs(b, H, Ht=None, Wt=None, seed=0, mode="default", rays=None):
-    """Build the reference-style ``input`` dict for ``b`` scenes, 2 context views.
+def make_inputs(b, H, Ht=None, Wt=None, seed=0, mode="default", rays=None, n_ctx=2):
+    """Build the reference-style ``input`` dict for ``b`` scenes, ``n_ctx`` context views (2 unless
+    stated; 1 keeps the first camera of the pair, 3 adds one below the baseline).
 
     mode: "default"  wide-baseline converging pair, query between them;
           "outside"  query far outside both frusta looking away (white rays,
@@ -62,9 +63,10 @@ def make_inputs(b, H, Ht=None, Wt=None, seed=0, mode="default", rays=None):
     Kq = make_intrinsics(Ht)
     ctx_c2w, qry_c2w = [], []
     for s in range(b):
-        jit = torch.randn(2, 3, generator=g, dtype=torch.float64) * 0.02
+        jit = torch.randn(max(2, n_ctx), 3, generator=g, dtype=torch.float64) * 0.02
         c0 = _trans(-0.3 + jit[0, 0], jit[0, 1], jit[0, 2]) @ _rot_y(+0.1)
         c1 = _trans(+0.3 + jit[1, 0], jit[1, 1], jit[1, 2]) @ _rot_y(-0.1)
+        c2 = _trans(jit[2, 0], -0.25 + jit[2, 1], 0.05 + jit[2, 2]) @ _rot_y(0.02) if n_ctx == 3 else None
         m = mode
         if mode == "mixed":
             m = ("default", "outside", "at_camera")[s % 3]
@@ -76,7 +78,7 @@ def make_inputs(b, H, Ht=None, Wt=None, seed=0, mode="default", rays=None):
             q = c0.clone() @ _rot_y(0.05)
         else:
             raise ValueError(mode)
-        ctx_c2w.append(torch.stack([c0, c1]))
+        ctx_c2w.append(torch.stack([c0, c1, c2][:n_ctx]))
         qry_c2w.append(q[None])
     ctx_c2w = torch.stack(ctx_c2w).float()
     qry_c2w = torch.stack(qry_c2w).float()
@@ -87,9 +89,9 @@ def make_inputs(b, H, Ht=None, Wt=None, seed=0, mode="default", rays=None):
     uv = uv[None, None].expand(b, 1, -1, -1).contiguous()
     return {
         "context": {
-            "rgb": torch.zeros(b, 2, H, H, 3),
+            "rgb": torch.zeros(b, n_ctx, H, H, 3),
             "cam2world": ctx_c2w,
-            "intrinsics": K[None, None].expand(b, 2, -1, -1).contiguous(),
+            "intrinsics": K[None, None].expand(b, n_ctx, -1, -1).contiguous(),
         },
         "query": {
             "cam2world": qry_c2w,

@@ -106,7 +106,7 @@ def prepare_cameras(inp):
     Returns a dict of fp32 tensors:
       Q     (b,n,4,4) inv(C) @ q            query cam2world in each ctx frame (models.py:208)
       Cself (b,n,4,4) inv(C) @ C            ~identity, passed to get_3d_point_epipolar (:207,283)
-      Rel   (b,2,n,4,4) Rel[:,k] = inv(C[:,k]) @ C   ctx-j -> ctx-k (:285-286)
+      Rel   (b,n,n,4,4) Rel[:,k] = inv(C[:,k]) @ C   ctx-j -> ctx-k (:285-286)
       qinv  (b,4,4)   inv(query cam2world)  (geometry.py:404 via models.py:586)
       K     (b,n,4,4) context intrinsics, Kq (b,4,4) query intrinsics
     """
@@ -116,7 +116,7 @@ def prepare_cameras(inp):
     out = {
         "Q": torch.matmul(Cinv, q),
         "Cself": torch.matmul(Cinv, C),
-        "Rel": torch.stack([torch.matmul(torch.inverse(C[:, k:k + 1]), C) for k in range(2)], dim=1),
+        "Rel": torch.stack([torch.matmul(torch.inverse(C[:, k:k + 1]), C) for k in range(C.shape[1])], dim=1),
         "qinv": torch.inverse(q[:, 0]),
         "K": inp["context"]["intrinsics"].clone(),
         "Kq": inp["query"]["intrinsics"][:, 0].clone(),
@@ -473,62 +473,164 @@ def render(sd, inp, z, H, W, P, interval=None, cams=None):
     interp = torch.cat([e0, e1], dim=-1)                              # (b,n,R,P,576)
     I["enc_v0"], I["enc_v1"] = e0, e1
     V = _lin(sd, "latent_value", interp)                              # models.py:487
-    Kk = _lin(sd, "key_map_2", F.relu(_lin(sd, "key_map", interp)))   # :491
     loc = local_coords(cams, d, o, pt, px, py)                        # :494-528
-    Q1 = _lin(sd, "query_embed_2", F.relu(_lin(sd, "query_embed", loc)))   # :529
-    I.update(value=V, key=Kk, q1=Q1, local=loc, pt=pt)
-
-    def joint_softmax(s):                                             # models.py:533-535
-        sj = s.permute(0, 2, 1, 3).reshape(b, R, n * P)
-        a = F.softmax(sj, dim=-1)
-        return a.reshape(b, R, n, P).permute(0, 2, 1, 3)
-    s1 = (Kk * Q1).sum(-1) / 16.                                      # :532
-    a1 = joint_softmax(s1)                                            # (b,n,R,P)
-    zsum = (V * a1[..., None]).sum(dim=3).sum(dim=1)                  # (b,R,288)  :537-540
-    g = _lin(sd, "encode_latent", zsum)                               # :548 (b,R,128)
-    qin = torch.cat([g[:, None, :, None, :].expand(-1, n, -1, P, -1), loc], dim=-1)   # :552
-    Q2 = _lin(sd, "query_repeat_embed_2", F.relu(_lin(sd, "query_repeat_embed", qin)))
-    s2 = (Q2 * Q1).sum(-1) / 16.                                      # :555
-    a2 = joint_softmax(s2)
-    zloc2 = (V * a2[..., None]).sum(dim=3) + zsum[:, None]            # :561  (b,n,R,288)
-    zfin = zloc2.sum(dim=1)                                           # :564
-    I.update(s1=s1, at_wt=a1, zsum=zsum, g=g, q2=Q2, s2=s2, at_wt2=a2, z_final=zfin)
-    # depth (models.py:573-594)
-    at_max = a1.argmax(dim=-1)                                        # (b,n,R)
-    w3d = (a1[..., None] * torch.clamp(pt, -100, 100)).sum(dim=3).sum(dim=1)    # (b,R,3)
-    qi = cams["qinv"]
-    zc = ((qi[:, 2, 0, None] * w3d[..., 0] + qi[:, 2, 1, None] * w3d[..., 1])
-          + qi[:, 2, 2, None] * w3d[..., 2]) + qi[:, 2, 3, None]
-    depth_ray = torch.clamp(zc, 0, 10)
-    # colour MLP (models.py:597-616; resnet_block_fc.py:132-168)
-    dd = torch.stack(d, dim=-1); mm = torch.stack(m, dim=-1)          # (b,n,R,3)
-    coords9 = torch.cat([dd, mm, o[:, :, None, :].expand(-1, -1, R, -1)], dim=-1)   # (b,n,R,9)
-    c18 = coords9.permute(0, 2, 1, 3).reshape(b, R, n * 9)
-    z576 = torch.cat([zfin, zfin], dim=-1)
-    x = _lin(sd, "phi.lin_in", c18)
-    for i in range(3):
-        x = x + _lin(sd, f"phi.lin_z.{i}", z576)
-        net = _lin(sd, f"phi.blocks.{i}.fc_0", F.relu(x))
-        x = x + _lin(sd, f"phi.blocks.{i}.fc_1", F.relu(net))
-    rgb = _lin(sd, "phi.lin_out", F.relu(x))
-    valid = overlaps.any(dim=1).float()                               # (b,R)
-    rgb = rgb * valid[..., None] + 1 * (1 - valid[..., None])
-    out = {
-        "rgb": rgb.reshape(b, 1, R, 3),
-        "valid_mask": valid[..., None],
-        "depth_ray": depth_ray[..., None],
-        "at_wt": a1.reshape(b * n, R, P),
-        "at_wts": [a1.reshape(b * n, R, P)],
-        "at_wt_max": at_max.reshape(b * n, R, 1),
+    out, I2 = _attention_and_colour(sd, cams, b, n, R, P, V, interp, loc, pt, d, m, o, overlaps)
+    I.update(I2)
+    I.update(value=V, local=loc, pt=pt)
+    out.update({
         "pixel_val": pv.reshape(b * n, R, P, 2),
-        "coords": coords9.reshape(b * n, R, 9),
         "uv": inp["query"]["uv"],
         "z": z,
         "_overlaps": overlaps,
         "_start": start, "_end": end,
         "_cams": cams,
         "_I": I,
-    }
+    })
+    return out
+
+
+def _attention_and_colour(sd, cams, b, n, R, P, V, interp_for_key, loc, pt, d, m, o, overlaps):
+    """Shared tail of every n_view branch (models.py:487-621): K, geometric Q, two joint-softmax
+    rounds over the ray's n*P samples, expected depth, colour MLP, white fill.  ``V`` already holds
+    latent_value(interp); returns (out entries, intermediates)."""
+    Kk = _lin(sd, "key_map_2", F.relu(_lin(sd, "key_map", interp_for_key)))   # :491
+    Q1 = _lin(sd, "query_embed_2", F.relu(_lin(sd, "query_embed", loc)))      # :529
+
+    def joint_softmax(s_):                                             # models.py:533-535
+        sj = s_.permute(0, 2, 1, 3).reshape(b, R, n * P)
+        a = F.softmax(sj, dim=-1)
+        return a.reshape(b, R, n, P).permute(0, 2, 1, 3)
+    s1 = (Kk * Q1).sum(-1) / 16.                                       # :532
+    a1 = joint_softmax(s1)
+    zsum = (V * a1[..., None]).sum(dim=3).sum(dim=1)                   # (b,R,L)  :537-540
+    g = _lin(sd, "encode_latent", zsum)                                # :548
+    qin = torch.cat([g[:, None, :, None, :].expand(-1, n, -1, P, -1), loc], dim=-1)   # :552
+    Q2 = _lin(sd, "query_repeat_embed_2", F.relu(_lin(sd, "query_repeat_embed", qin)))
+    s2 = (Q2 * Q1).sum(-1) / 16.                                       # :555
+    a2 = joint_softmax(s2)
+    zloc2 = (V * a2[..., None]).sum(dim=3) + zsum[:, None]             # :561  (b,n,R,L)
+    zfin = zloc2.sum(dim=1)                                            # :564: every ctx row holds this sum
+    at_max = a1.argmax(dim=-1)
+    w3d = (a1[..., None] * torch.clamp(pt, -100, 100)).sum(dim=3).sum(dim=1)
+    qi = cams["qinv"]
+    zc = ((qi[:, 2, 0, None] * w3d[..., 0] + qi[:, 2, 1, None] * w3d[..., 1])
+          + qi[:, 2, 2, None] * w3d[..., 2]) + qi[:, 2, 3, None]
+    depth_ray = torch.clamp(zc, 0, 10)
+    dd = torch.stack(d, dim=-1); mm = torch.stack(m, dim=-1)
+    coords9 = torch.cat([dd, mm, o[:, :, None, :].expand(-1, -1, R, -1)], dim=-1)    # (b,n,R,9)
+    cflat = coords9.permute(0, 2, 1, 3).reshape(b, R, n * 9)          # :602
+    zcat = torch.cat([zfin] * n, dim=-1)                               # :605-606 (identical copies per ctx)
+    x = _lin(sd, "phi.lin_in", cflat)
+    for i in range(3):
+        x = x + _lin(sd, f"phi.lin_z.{i}", zcat)
+        net = _lin(sd, f"phi.blocks.{i}.fc_0", F.relu(x))
+        x = x + _lin(sd, f"phi.blocks.{i}.fc_1", F.relu(net))
+    rgb = _lin(sd, "phi.lin_out", F.relu(x))
+    valid = overlaps.any(dim=1).float()
+    rgb = rgb * valid[..., None] + 1 * (1 - valid[..., None])
+    out = {"rgb": rgb.reshape(b, 1, R, 3), "valid_mask": valid[..., None], "depth_ray": depth_ray[..., None],
+           "at_wt": a1.reshape(b * n, R, P), "at_wts": [a1.reshape(b * n, R, P)],
+           "at_wt_max": at_max.reshape(b * n, R, 1), "coords": coords9.reshape(b * n, R, 9)}
+    I = dict(key=Kk, q1=Q1, s1=s1, at_wt=a1, zsum=zsum, g=g, q2=Q2, s2=s2, at_wt2=a2, z_final=zfin)
+    return out, I
+
+
+def render_single_view(sd, inp, z, H, W, P, interval=None, cams=None):
+    """``n_view = 1`` branch of the reference forward (models.py:478-485 + the shared tail): one
+    context view, no cross-view gather; the 576 gathered channels and
+    [tanh(pt/5), tanh(pt/100)] go through ``update_val_merge`` (582 -> 576, no ReLU), V / K are
+    576-wide, the softmax runs over the P samples of the single line, phi sees 9 + 576 inputs.
+    ORACLE ONLY in this round: the CUDA path covers n_view = 2."""
+    dev = z[0].device
+    b, n = inp["context"]["cam2world"].shape[:2]
+    assert n == 1
+    uv = inp["query"]["uv"][:, 0]
+    R = uv.shape[1]
+    if cams is None:
+        cams = prepare_cameras(inp)
+    if interval is None:
+        interval = torch.linspace(0, 1, P, device=dev)
+    d, m, o = ray_setup(cams, uv)
+    start, end, overlaps = epipolar_segment(cams, d, o, H)
+    pv = line_samples(start, end, interval)                           # (b,1,R,P,2)
+    gx, gy = pv[..., 0], pv[..., 1]
+    flat = lambda t: t.reshape(b * n, *t.shape[2:])
+    f_own = gather_bilinear(z, flat(gx), flat(gy), border=True).reshape(b, n, R, P, -1)
+    pt, px, py = triangulate(cams, d, m, pv, H, W)                    # NaN/Inf already scrubbed (:126-127,481)
+    pt_context = torch.cat([torch.tanh(pt / 5.), torch.tanh(pt / 100.)], dim=-1)      # :483
+    interp = _lin(sd, "update_val_merge", torch.cat([f_own, pt_context], dim=-1))     # :484-485
+    V = _lin(sd, "latent_value", interp)                              # :487
+    loc = local_coords(cams, d, o, pt, px, py)
+    out, I = _attention_and_colour(sd, cams, b, n, R, P, V, interp, loc, pt, d, m, o, overlaps)
+    I.update(pixel_val=pv, feat_primary=f_own, merged=interp, value=V, local=loc, pt=pt)
+    out.update({"pixel_val": pv.reshape(b * n, R, P, 2), "uv": inp["query"]["uv"], "z": z,
+                "_overlaps": overlaps, "_cams": cams, "_I": I})
+    return out
+
+
+def _project_to_grid(ptk, Kj, H, W):
+    """geometry.project (geometry.py:374-393) with view j's intrinsics, then
+    util.normalize_for_grid_sample (utils/util.py:16-19).  ptk (b,R,P,3), Kj (b,4,4)."""
+    fx = Kj[:, 0, 0][:, None, None]; fy = Kj[:, 1, 1][:, None, None]
+    cx = Kj[:, 0, 2][:, None, None]; cy = Kj[:, 1, 2][:, None, None]
+    X, Y, Z = ptk[..., 0], ptk[..., 1], ptk[..., 2]
+    xp = fx * X / (Z + 1e-12) + cx
+    yp = fy * Y / (Z + 1e-12) + cy
+    big = torch.full_like(xp, 1e10)
+    xp = torch.where(torch.isfinite(xp), xp, big)
+    yp = torch.where(torch.isfinite(yp), yp, big)
+    return (xp / (W - 1)) * 2 - 1, (yp / (H - 1)) * 2 - 1
+
+
+def render_three_views(sd, inp, z, H, W, P, interval=None, cams=None):
+    """``n_view = 3`` branch of the reference forward (models.py:345-475 + the shared tail).
+    What the code does (followed literally, including its frame bookkeeping): with
+    ptv[a][j] = the samples of context j's epipolar line expressed in view a's frame
+    (models.py:354-382), the row (ray r, sample p) of context a is encoded from
+      k = 0: its own gathered features and tanh(ptv[a][a] / 5)                       (:436-439)
+      k = 1, 2 (the other contexts j in ascending order): view j's maps sampled (zero padding)
+             at project(ptv[a][j], K_j) - i.e. the (r, p) sample of context j's OWN line - and
+             tanh(ptv[a][j] / 5)                                                      (:385-423, 437)
+    each through query_encode_latent(_2); the three 288-vectors are interleaved channel-major
+    (channel c of part k at index 3c + k: ``cat(dim=2).flatten(1, 2)``, :444-446).
+    ORACLE ONLY in this round: the CUDA path covers n_view = 2."""
+    dev = z[0].device
+    b, n = inp["context"]["cam2world"].shape[:2]
+    assert n == 3
+    uv = inp["query"]["uv"][:, 0]
+    R = uv.shape[1]
+    if cams is None:
+        cams = prepare_cameras(inp)
+    if interval is None:
+        interval = torch.linspace(0, 1, P, device=dev)
+    d, m, o = ray_setup(cams, uv)
+    start, end, overlaps = epipolar_segment(cams, d, o, H)
+    pv = line_samples(start, end, interval)                           # (b,3,R,P,2)
+    gx, gy = pv[..., 0], pv[..., 1]
+    flat = lambda t: t.reshape(b * n, *t.shape[2:])
+    f_own = gather_bilinear(z, flat(gx), flat(gy), border=True).reshape(b, n, R, P, -1)
+    pt, px, py = triangulate(cams, d, m, pv, H, W)                    # (b,3,R,P,3), ctx j's samples in frame j
+    Rel, K = cams["Rel"], cams["K"]                                   # Rel[:, a, j]: frame j -> frame a
+    zmaps = [t.reshape(b, n, *t.shape[1:]) for t in z]
+    enc = lambda x: _lin(sd, "query_encode_latent_2", F.relu(_lin(sd, "query_encode_latent", x)))
+    rows = []
+    for a in range(n):
+        ptv_a = _xform_point(Rel[:, a], pt)                           # (b,3,R,P,3): [j] = ctx j's samples in frame a
+        parts = [enc(torch.cat([f_own[:, a], torch.tanh(_nan_to_num(ptv_a[:, a]) / 5.)], dim=-1))]
+        for j in range(n):
+            if j == a:
+                continue
+            gxc, gyc = _project_to_grid(ptv_a[:, j], K[:, j], H, W)  # :394-401 (intrinsics of view j)
+            f_j = gather_bilinear([t[:, j] for t in zmaps], gxc, gyc, border=False)        # :403-404
+            parts.append(enc(torch.cat([f_j, torch.tanh(_nan_to_num(ptv_a[:, j]) / 5.)], dim=-1)))
+        rows.append(torch.stack(parts, dim=-1).flatten(-2, -1))       # (b,R,P,288*3), index 3c + k
+    interp = torch.stack(rows, dim=1)                                 # (b,3,R,P,864)  :473
+    V = _lin(sd, "latent_value", interp)
+    loc = local_coords(cams, d, o, pt, px, py)
+    out, I = _attention_and_colour(sd, cams, b, n, R, P, V, interp, loc, pt, d, m, o, overlaps)
+    I.update(pixel_val=pv, feat_primary=f_own, interp=interp, value=V, local=loc, pt=pt)
+    out.update({"pixel_val": pv.reshape(b * n, R, P, 2), "uv": inp["query"]["uv"], "z": z,
+                "_overlaps": overlaps, "_cams": cams, "_I": I})
     return out
 
 
