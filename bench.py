@@ -412,13 +412,21 @@ def main():
         rps, dt = cpu_oracle_rays_per_s(H, P, args.cpu_rays, 128)
         cpu_base = {"value": rps, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
                     "sample": f"{args.cpu_rays} rays of one {H}x{H}/{P}-sample scene, {dt:.1f} s"}
+    maps = "bf16 maps" if args.precision == "bf16" else "fp32 maps"
+    if (H, P) == (256, 64):
+        tag = "BASELINE config 3 layout: 12 scenes per GPU" if args.precision == "bf16" else "BASELINE config 2"
+    elif (H, P) == (512, 128):
+        tag = "BASELINE config 4"
+    else:
+        tag = "non-BASELINE size"
+    workload = f"{H}x{H} target, 2 views, {P} samples, {maps}, {b} scenes per GPU ({tag})"
     line = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32_simt": "f32", "fp32": "f32 (3xbf16 tcgen05 split, fp32 accumulate)", "bf16": "bf16"}[args.precision],
         "data": "synthetic",
-        "config": {"workload": f"{H}x{H} target, 2 views, {P} samples, fp32 maps, {b} scenes per GPU (BASELINE config 2)",
+        "config": {"workload": workload,
                    "scenes_per_gpu": b, "rays_per_step": total_rays, "precision": args.precision,
                    "parallelism": f"ray/scene sharding x{world}, all_gather of tiles",
                    "l2": "inputs (feature maps %.0f MB per GPU) exceed the 126 MB L2" % (sum(t_.numel() * 4 for t_ in z_h) / 1e6),
