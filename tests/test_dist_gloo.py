@@ -122,3 +122,38 @@ def test_flat_gradient_allreduce_gloo(world, average):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res), res
+
+
+def _sync_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "experiment_scripts"))
+    import _common as C
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(100 + rank)                      # every rank starts from different weights
+        model = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
+        C.sync_model(model)
+        flat = torch.cat([p.data.reshape(-1) for p in model.parameters()])
+        ref = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(ref, flat)
+        q.put((rank, all(torch.equal(r, ref[0]) for r in ref), None))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sync_model_flat_broadcast_gloo():
+    """Driver start-up: rank 0's weights reach every rank (train_realestate10k.py:60-62) in one broadcast."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sync_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res), res
