@@ -19,13 +19,15 @@ LOCAL = 16               # local_coords channels, models.py:528
 D_IN_PHI_PER_VIEW = 9    # plucker(6) + origin(3), models.py:144,597
 
 
-def renderer_param_shapes(n_view=2, num_hidden_units_phi=128):
+def renderer_param_shapes(n_view=2, num_hidden_units_phi=128, no_latent_concat=False):
     """Ordered {name: shape} of every non-encoder parameter (models.py:96-145)."""
     if n_view not in (1, 2, 3):
         raise NotImplementedError("the reference defines n_view in {1, 2, 3}")
     # n_view > 1: the per-sample encoder halves the latent (models.py:100-104); n_view == 1 keeps the
     # 576 channels and merges the 6 point channels with update_val_merge (models.py:107-108)
-    LATENT = LATENT_IN // 2 if n_view > 1 else LATENT_IN
+    LATENT = LATENT_IN // 2 if (n_view > 1 and not no_latent_concat) else LATENT_IN
+    # no_latent_concat: no per-sample encoder, raw 576-channel features, V / K read one view (models.py:106-107,121-124)
+    kv_in = LATENT if no_latent_concat else LATENT * n_view
     h = HIDDEN
     hp = num_hidden_units_phi
     s = OrderedDict()
@@ -35,14 +37,16 @@ def renderer_param_shapes(n_view=2, num_hidden_units_phi=128):
         s[name + ".bias"] = (cout,)
 
     conv2d("conv_map", 3, 64, 7)                                  # models.py:96
-    if n_view > 1:
+    if no_latent_concat:
+        conv2d("feature_map", LATENT_IN, LATENT_IN // 2)          # :107 (defined, never evaluated)
+    elif n_view > 1:
         conv2d("query_encode_latent", LATENT_IN + 3, LATENT_IN)   # :102
         conv2d("query_encode_latent_2", LATENT_IN, LATENT)        # :103
         conv2d("update_val_merge", LATENT * 2 + 6, LATENT)        # :105
     else:
         conv2d("update_val_merge", LATENT + 6, LATENT)            # :108
-    conv2d("latent_value", LATENT * n_view, LATENT)               # :117
-    conv2d("key_map", LATENT * n_view, h)                         # :118
+    conv2d("latent_value", kv_in, LATENT)                         # :117 / :122
+    conv2d("key_map", kv_in, h)                                   # :118 / :123
     conv2d("key_map_2", h, h)                                     # :119
     conv2d("query_embed", LOCAL, h)                               # :126
     conv2d("query_embed_2", h, h)                                 # :127

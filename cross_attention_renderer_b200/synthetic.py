@@ -112,7 +112,7 @@ def make_features(b, H, seed=0, n_view=2, dtype=torch.float32):
     return [z1.to(dtype), z2.to(dtype), z3.to(dtype)]
 
 
-def make_state_dict(seed=0, peaky=False, n_view=2):
+def make_state_dict(seed=0, peaky=False, n_view=2, no_latent_concat=False):
     """Every renderer parameter re-randomised: W ~ N(0, 1/sqrt(fan_in)),
     b ~ N(0, 0.1).  (The reference's default init zeroes phi.blocks.*.fc_1,
     resnet_block_fc.py:39, which would hide bugs in those layers.)
@@ -120,7 +120,7 @@ def make_state_dict(seed=0, peaky=False, n_view=2):
     uniform."""
     g = torch.Generator().manual_seed(3000 + seed)
     sd = {}
-    for name, shape in renderer_param_shapes(n_view).items():
+    for name, shape in renderer_param_shapes(n_view, no_latent_concat=no_latent_concat).items():
         if name.endswith(".weight"):
             fan_in = 1
             for d in shape[1:]:

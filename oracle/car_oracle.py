@@ -1,8 +1,10 @@
 """ORACLE — test infrastructure, NOT product code.
 
 CPU (or any torch device) restatement of the reference's per-ray rendering
-path ``CrossAttentionRenderer.forward(input, z=z)`` for n_view=2 with default
-flags (reference models.py:190-626).  Only ``tests/``,
+path ``CrossAttentionRenderer.forward(input, z=z)`` (reference models.py:190-626):
+``render`` is the n_view=2 hot path (plus its ``no_sample`` / ``no_latent_concat``
+ablations), ``render_single_view`` / ``render_three_views`` the other branches - those
+and the ablations are oracle-only so far (tests/test_oracle_nview.py).  Only ``tests/``,
 ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl
 reference`` leg may import this file; the product
 (``cross_attention_renderer_b200``) never does.
@@ -433,10 +435,16 @@ def _nan_to_num(x):
     return torch.nan_to_num(x, 0)                                     # models.py:322-325
 
 
-def render(sd, inp, z, H, W, P, interval=None, cams=None):
+def render(sd, inp, z, H, W, P, interval=None, cams=None, no_sample=False, no_latent_concat=False):
     """Full hot path.  sd: renderer state_dict (fp32), inp: reference-style input
     dict, z: [z1,z2,z3] NCHW.  Returns dict with every out_dict entry of the
-    reference (models.py:217-218,570-571,592-597,617-624) and the intermediates."""
+    reference (models.py:217-218,570-571,592-597,617-624) and the intermediates.
+
+    Ablation branches (ORACLE ONLY in this round; the CUDA path runs the default flags):
+      no_sample         epipolar line = the query ray's points at depths linspace(0.1, 10, P) projected
+                        into each context (geometry.get_epipolar_lines_volumetric :165-187), no clipping
+      no_latent_concat  no cross-view gather / per-sample encoder: the raw 576 gathered channels feed
+                        latent_value / key_map directly (models.py:476-477,121-124)"""
     dev = z[0].device
     b, n = inp["context"]["cam2world"].shape[:2]
     assert n == 2
@@ -448,14 +456,40 @@ def render(sd, inp, z, H, W, P, interval=None, cams=None):
         interval = torch.linspace(0, 1, P, device=dev)                # models.py:261
     I = {}
     d, m, o = ray_setup(cams, uv)
-    start, end, overlaps = epipolar_segment(cams, d, o, H)
-    pv = line_samples(start, end, interval)                           # (b,n,R,P,2)
+    if no_sample:
+        # geometry.py:165-187: same elementwise torch ops in the same order as the reference (plain fp32)
+        ivl = torch.linspace(0.1, 10., P, device=dev)
+        dvec = torch.stack(d, dim=-1)                                 # (b,n,R,3)
+        pts = o[:, :, None, None, :] + ivl[None, None, None, :, None] * dvec[..., None, :]
+        Kc = cams["K"]
+        fx = Kc[..., 0, 0][..., None, None]; fy = Kc[..., 1, 1][..., None, None]
+        cx = Kc[..., 0, 2][..., None, None]; cy = Kc[..., 1, 2][..., None, None]
+        xp = fx * pts[..., 0] / (pts[..., 2] + 1e-12) + cx            # geometry.project :386-387
+        yp = fy * pts[..., 1] / (pts[..., 2] + 1e-12) + cy
+        big = torch.full_like(xp, 1e10)
+        xp = torch.where(torch.isfinite(xp), xp, big)                 # :390-391
+        yp = torch.where(torch.isfinite(yp), yp, big)
+        pv = torch.stack([(xp / (W - 1)) * 2 - 1, (yp / (H - 1)) * 2 - 1], dim=-1)   # utils/util.py:16-19
+        start, end = pv[..., 0, :], pv[..., -1, :]
+        overlaps = ((pv < 1) & (pv > -1)).all(dim=-1).any(dim=-1)     # :185 ("no_intersect")
+    else:
+        start, end, overlaps = epipolar_segment(cams, d, o, H)
+        pv = line_samples(start, end, interval)                       # (b,n,R,P,2)
     I["pixel_val"] = pv
     gx, gy = pv[..., 0], pv[..., 1]
     zmaps = [t.reshape(b, n, *t.shape[1:]) for t in z]
     flat = lambda t: t.reshape(b * n, *t.shape[2:])
     f_own = gather_bilinear(z, flat(gx), flat(gy), border=True).reshape(b, n, R, P, -1)
     pt, px, py = triangulate(cams, d, m, pv, H, W)
+    if no_latent_concat:
+        V = _lin(sd, "latent_value", f_own)                           # models.py:476-477,487
+        loc = local_coords(cams, d, o, pt, px, py)
+        out, I2 = _attention_and_colour(sd, cams, b, n, R, P, V, f_own, loc, pt, d, m, o, overlaps)
+        I.update(I2)
+        I.update(feat_primary=f_own, value=V, local=loc, pt=pt)
+        out.update({"pixel_val": pv.reshape(b * n, R, P, 2), "uv": inp["query"]["uv"], "z": z,
+                    "_overlaps": overlaps, "_start": start, "_end": end, "_cams": cams, "_I": I})
+        return out
     pt_v0, pt_v1, gxc, gyc = reproject(cams, pt, H, W)
     I["grid_cross"] = torch.stack([gxc, gyc], dim=-1)
     # features of the OTHER view at the reprojected point (models.py:316-320)

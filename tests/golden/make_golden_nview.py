@@ -21,6 +21,9 @@ CASES = {
     "nview1_mixed": dict(n_view=1, b=3, H=32, Ht=8, P=8, seed=6, mode="mixed", peaky=False),
     "nview3_default": dict(n_view=3, b=2, H=32, Ht=8, P=8, seed=7, mode="default", peaky=True),
     "nview3_mixed": dict(n_view=3, b=3, H=32, Ht=6, P=8, seed=8, mode="mixed", peaky=False),
+    "nview2_nosample": dict(n_view=2, b=2, H=32, Ht=8, P=16, seed=9, mode="mixed", peaky=True, no_sample=True),
+    "nview2_nolatentconcat": dict(n_view=2, b=2, H=32, Ht=8, P=8, seed=10, mode="default", peaky=True,
+                                  no_latent_concat=True),
 }
 
 
@@ -31,12 +34,14 @@ def run_case(ref_models, cfg):
     nv = cfg["n_view"]
     inp = synthetic.make_inputs(cfg["b"], cfg["H"], cfg["Ht"], seed=cfg["seed"], mode=cfg["mode"], n_ctx=nv)
     z = synthetic.make_features(cfg["b"], cfg["H"], seed=cfg["seed"], n_view=nv)
-    sd = synthetic.make_state_dict(seed=cfg["seed"], peaky=cfg["peaky"], n_view=nv)
+    nlc, nos = cfg.get("no_latent_concat", False), cfg.get("no_sample", False)
+    sd = synthetic.make_state_dict(seed=cfg["seed"], peaky=cfg["peaky"], n_view=nv, no_latent_concat=nlc)
     torch.manual_seed(0)
-    m = ref_models.CrossAttentionRenderer(model="midas_vit", n_view=nv, npoints=cfg["P"])
+    m = ref_models.CrossAttentionRenderer(model="midas_vit", n_view=nv, npoints=cfg["P"], no_sample=nos,
+                                          no_latent_concat=nlc)
     # the checkpoint ABI restated in params.py must be the reference module's own parameter list
     ref_shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.startswith("encoder.")}
-    assert ref_shapes == {k: tuple(v) for k, v in renderer_param_shapes(nv).items()}, "params.py != reference"
+    assert ref_shapes == {k: tuple(v) for k, v in renderer_param_shapes(nv, no_latent_concat=nlc).items()}, "params.py != reference"
     missing, unexpected = m.load_state_dict(sd, strict=False)
     assert not unexpected and all(k.startswith("encoder.") for k in missing)
     m.eval()

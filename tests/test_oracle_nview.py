@@ -22,18 +22,18 @@ def load(name):
     nv = cfg["n_view"]
     inp = synthetic.make_inputs(cfg["b"], cfg["H"], cfg["Ht"], seed=cfg["seed"], mode=cfg["mode"], n_ctx=nv)
     z = synthetic.make_features(cfg["b"], cfg["H"], seed=cfg["seed"], n_view=nv)
-    sd = synthetic.make_state_dict(seed=cfg["seed"], peaky=cfg["peaky"], n_view=nv)
+    sd = synthetic.make_state_dict(seed=cfg["seed"], peaky=cfg["peaky"], n_view=nv,
+                                   no_latent_concat=cfg.get("no_latent_concat", False))
     return cfg, rec, inp, z, sd
 
 
 @pytest.mark.parametrize("name", CASES)
 def test_other_branches_match_reference(name):
     cfg, rec, inp, z, sd = load(name)
-    fn = {1: orc.render_single_view, 3: getattr(orc, "render_three_views", None)}[cfg["n_view"]]
-    if fn is None:
-        pytest.skip("n_view = 3 oracle not written yet")
+    fn = {1: orc.render_single_view, 2: orc.render, 3: orc.render_three_views}[cfg["n_view"]]
+    kw = {k: True for k in ("no_sample", "no_latent_concat") if cfg.get(k)}
     with torch.no_grad():
-        out = fn(sd, inp, z, cfg["H"], cfg["H"], cfg["P"])
+        out = fn(sd, inp, z, cfg["H"], cfg["H"], cfg["P"], **kw)
     t = lambda k: torch.from_numpy(rec["out_" + k])
     assert torch.equal(out["valid_mask"], t("valid_mask"))
     # sample coordinates: the reference's library matmuls round differently from the fixed-order oracle
