@@ -442,3 +442,27 @@ def test_empty_shard_is_a_no_op():
     part = run_cuda(m, inp, z, ray_range=(2, 5))
     assert torch.equal(part["rgb"][:, :, 2:5], full["rgb"][:, :, 2:5])
     assert float(part["rgb"][:, :, :2].abs().sum()) == 0.0
+
+
+def test_forward_contract_inputs_untouched_and_passthroughs():
+    """Boundary contract: the caller's ``input`` and ``z`` are not mutated (the reference
+    deep-copies, models.py:193), ``uv`` / ``z`` are passed through, ``pixel_val`` comes back on the host
+    (models.py:570), ``at_wts`` is the list holding ``at_wt``."""
+    b, H, P = 2, 32, 64
+    inp = synthetic.to_device(synthetic.make_inputs(b, H, 8, seed=70), DEV)
+    z = [t.to(DEV) for t in synthetic.make_features(b, H, seed=70)]
+    snap_inp = {k: {kk: vv.clone() for kk, vv in v.items()} for k, v in inp.items()}
+    snap_z = [t.clone() for t in z]
+    m = make_model(synthetic.make_state_dict(seed=70), P, H, precision="fp32")
+    with torch.no_grad():
+        out = m(inp, z=z)
+    torch.cuda.synchronize()
+    for k, v in inp.items():
+        for kk, vv in v.items():
+            assert torch.equal(vv, snap_inp[k][kk]), (k, kk)
+    assert all(torch.equal(a, c) for a, c in zip(z, snap_z))
+    assert out["z"] is z and out["uv"] is inp["query"]["uv"]
+    assert out["pixel_val"].device.type == "cpu" and out["rgb"].device.type == "cuda"
+    assert isinstance(out["at_wts"], list) and out["at_wts"][0] is out["at_wt"]
+    assert out["at_wt_max"].dtype == torch.int64 and out["at_wt_max"].shape == (b * 2, 64, 1)
+    assert out["coords"].shape == (b * 2, 64, 9) and out["valid_mask"].shape == (b, 64, 1)
