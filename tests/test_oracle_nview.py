@@ -46,3 +46,35 @@ def test_other_branches_match_reference(name):
     top2 = aw.topk(2, dim=-1).values
     decided = (top2[..., 0] - top2[..., 1]) > 1e-4 * top2[..., 0]
     assert torch.equal(out["at_wt_max"][..., 0][decided], t("at_wt_max")[..., 0][decided])
+
+
+def test_epipolar_clipping_on_degenerate_rays():
+    """epipolar.project_rays (called directly in the unmodified reference, make_golden_rays.py) on rays
+    through / behind / beside the camera and directions parallel to the image plane: the oracle's
+    fixed-order restatement must make the same validity decisions and the same segment end points
+    (after the NaN / Inf scrub of models.py:246-252)."""
+    rec = dict(np.load(os.path.join(GOLD, "rays_degenerate.npz")))
+    H = int(rec["H"])
+    o = torch.from_numpy(rec["origins"])                   # (B,3): one origin per "scene", n = 1
+    d = torch.from_numpy(rec["dirs"])                      # (R,3)
+    B, R = o.shape[0], d.shape[0]
+    cams = {"K": torch.from_numpy(rec["K"])[None, None].expand(B, 1, 4, 4).contiguous()}
+    dd = tuple(d[:, i][None, None].expand(B, 1, R).contiguous() for i in range(3))
+    start, end, overlaps = orc.epipolar_segment(cams, dd, o[:, None, :], H)
+
+    def grid(xy):
+        g = (torch.from_numpy(xy) - 0.5) * 2
+        return torch.where(torch.isfinite(g), g, torch.zeros_like(g))
+    assert torch.equal(overlaps[:, 0], torch.from_numpy(rec["overlaps"]))
+    ref_s, ref_e = grid(rec["xy_min"]), grid(rec["xy_max"])
+    ov = overlaps[:, 0]
+    # rays that overlap the image: end points agree to fp32 rounding of a differently ordered 3x3 product
+    assert float((start[:, 0][ov] - ref_s[ov]).abs().max()) < 2e-5
+    assert float((end[:, 0][ov] - ref_e[ov]).abs().max()) < 2e-5
+    # rays that do not: the garbage-but-deterministic coordinates still feed the joint softmax when the
+    # other context is valid, so they must agree too (same +-inf / NaN flow, same first-index tie-break)
+    fin = torch.isfinite(ref_s).all(-1) & torch.isfinite(ref_e).all(-1)
+    big = (ref_s.abs().max(-1).values < 1e4) & (ref_e.abs().max(-1).values < 1e4)
+    sel = ~ov & fin & big
+    assert float((start[:, 0][sel] - ref_s[sel]).abs().max()) < 1e-3
+    assert float((end[:, 0][sel] - ref_e[sel]).abs().max()) < 1e-3
