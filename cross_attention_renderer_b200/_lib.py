@@ -8,7 +8,7 @@ cross_attention_renderer_b200/csrc``).
 import ctypes as C
 import os
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 PREC_FP32_SIMT, PREC_FP32_3XBF16, PREC_BF16 = 0, 1, 2
 PRECISIONS = {"fp32_simt": PREC_FP32_SIMT, "fp32": PREC_FP32_3XBF16, "bf16": PREC_BF16}
 K_ENC = 592
@@ -56,7 +56,7 @@ class car_render_args(C.Structure):
                 ("at_wt_max", c_fp), ("pixel_val", c_fp), ("coords", c_fp),
                 ("workspace", c_fp), ("workspace_bytes", C.c_size_t),
                 ("debug", car_debug), ("stream", c_fp), ("use_fused", C.c_int32),
-                ("train", C.c_int32)]
+                ("train", C.c_int32), ("chunk_rays", C.c_int32)]
 
 
 class car_mat_grad(C.Structure):
@@ -97,12 +97,16 @@ SYMBOLS = {
     "car_profile_begin": (C.c_int, []),
     "car_profile_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]),
     "car_debug_set_fused_stats": (C.c_int, [c_fp]),
-    "car_mma_rate_test": (C.c_int, [C.c_int] * 7 + [c_fp, c_fp]),
     "car_gemm_umma_test": (C.c_int, [c_fp] * 6 + [C.c_int] * 5 + [c_fp]),
+}
+# include/car_b200_test.h (libcar_b200_test.so: micro-benchmarks / building-block kernels, not the product)
+TEST_SYMBOLS = {
+    "car_mma_rate_test": (C.c_int, [C.c_int] * 7 + [c_fp, c_fp]),
     "car_gemm_pair_test": (C.c_int, [c_fp] * 7 + [C.c_int] * 8 + [c_fp]),
 }
 
 _lib = None
+_test_lib = None
 
 
 def lib_path():
@@ -127,6 +131,25 @@ def load():
     if got != ABI_VERSION:
         raise RuntimeError(f"libcar_b200.so ABI {got} != binding ABI {ABI_VERSION}; rebuild")
     _lib = lib
+    return lib
+
+
+def load_test():
+    """dlopen libcar_b200_test.so (test / micro-benchmark kernels); the product library is loaded first."""
+    global _test_lib
+    if _test_lib is not None:
+        return _test_lib
+    load()
+    path = os.path.join(os.path.dirname(_LIB_PATH), "libcar_b200_test.so")
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found: build with `make -C cross_attention_renderer_b200/csrc`")
+    lib = C.CDLL(path)
+    for name, (res, args) in TEST_SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    lib.car_last_error = _lib.car_last_error
+    _test_lib = lib
     return lib
 
 

@@ -25,6 +25,14 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+int sm_count() {
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) { int n = 0; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }
+  if (!cache[dev]) cudaDeviceGetAttribute(&cache[dev], cudaDevAttrMultiProcessorCount, dev);
+  return cache[dev];
+}
 
 // ---- optional per-stage event timing -------------------------------------------------
 struct ProfRec { cudaEvent_t a, b; int stage; };
@@ -277,7 +285,8 @@ int car_render_forward(const car_render_args *pa) {
   if ((a.debug.interp && (a.use_fused & 1)) || ((a.debug.key || a.debug.q2) && (a.use_fused & 2))) {
     set_error("debug taps interp/key/q2 need the unfused stages: clear the matching use_fused bits"); return -10;
   }
-  int chunk = car_default_chunk_rays(a.precision, a.P, a.use_fused);
+  if (a.chunk_rays < 0) { set_error("bad chunk_rays %d", a.chunk_rays); return -3; }
+  int chunk = a.chunk_rays > 0 ? a.chunk_rays : car_default_chunk_rays(a.precision, a.P, a.use_fused);
   int span = a.ray_end - a.ray_begin;
   if (chunk > span) chunk = span;
   const int use_fused = a.train ? 0 : a.use_fused;
@@ -292,7 +301,8 @@ int car_render_forward(const car_render_args *pa) {
       return -8;
     }
   }
-  while (chunk > 1 && carve(nullptr, a.precision, a.P, chunk, use_fused, a.train).bytes > a.workspace_bytes) chunk = (chunk + 1) / 2;
+  // an explicit chunk is honoured exactly; the default is halved until it fits the given workspace
+  while (a.chunk_rays == 0 && chunk > 1 && carve(nullptr, a.precision, a.P, chunk, use_fused, a.train).bytes > a.workspace_bytes) chunk = (chunk + 1) / 2;
   if (carve(nullptr, a.precision, a.P, chunk, use_fused, a.train).bytes > a.workspace_bytes) { set_error("workspace too small: %zu bytes", a.workspace_bytes); return -8; }
   Workspace w = carve((char *)a.workspace, a.precision, a.P, chunk, use_fused, a.train);
   cudaStream_t st = (cudaStream_t)a.stream;

@@ -26,6 +26,7 @@ namespace car {
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
+int sm_count();                     // multiprocessors of the CURRENT device (cached per device)
 // Profiling hooks (car_profile_begin/end): call around a kernel launch.
 void prof_pre(int stage, cudaStream_t st);
 void prof_post(cudaStream_t st);

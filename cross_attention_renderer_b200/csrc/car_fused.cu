@@ -633,8 +633,7 @@ int launch_fused_encode(const car_render_args &a, int g0, int g1, const float *g
   if (nb < 2) { set_error("fused encode: not enough shared memory"); return -21; }
   p.nb = nb;
   const size_t smem = fixed + (size_t)nb * b_stage;
-  static int sms = 0;
-  if (!sms) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int sms = sm_count();
   int pairs = sms / 2;
   if (pairs > (g1 - g0) * p.hpr) pairs = (g1 - g0) * p.hpr;
   static int cl_env = -1;

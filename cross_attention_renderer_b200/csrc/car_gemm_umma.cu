@@ -412,8 +412,7 @@ int launch_gemm_umma(const uint16_t *a_hi, const uint16_t *a_lo, int lda, const 
   p.add_src = epi.accumulate ? out.f32_add : nullptr;
   p.out_f32 = out.f32; p.out_hi = out.hi; p.out_lo = out.lo; p.ldc = out.ldc;
   size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
-  static int sms = 0;
-  if (!sms) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int sms = sm_count();
   int tiles = ((M + BM - 1) / BM) * (N / BN);
   int grid = tiles < sms ? tiles : sms;
   cudaError_t e;

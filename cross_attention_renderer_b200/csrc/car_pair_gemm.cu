@@ -182,35 +182,9 @@ k_pair_gemm(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-
 }  // namespace
 
-int make_tmap_bf16(CUtensorMap *tm, const uint16_t *base, int rows, int K, int ld, int box_rows, int box_k) {
-  static EncodeTiledFn enc = nullptr;
-  if (!enc) {
-    void *ptr = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      enc = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return -10; }
-  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUtensorMapSwizzle sw = box_k * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                          : (box_k * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t *>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d (rows=%d K=%d ld=%d box=%dx%d)", (int)r, rows, K, ld, box_rows, box_k); return -11; }
-  return 0;
-}
+int make_tmap_bf16(CUtensorMap *tm, const uint16_t *base, int rows, int K, int ld, int box_rows, int box_k);
 
 }  // namespace car
 

@@ -590,8 +590,7 @@ int launch_tail(const car_render_args &a, int phase, int g0, int g1, const float
   if (nb < 2) { set_error("tail: not enough shared memory"); return -31; }
   p.nb = nb;
   const size_t smem = fixed + (size_t)nb * bstage;
-  static int sms = 0;
-  if (!sms) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int sms = sm_count();
   const int grid = nrays < sms ? nrays : sms;
   cudaError_t e = cudaSuccess;
   prof_pre(CAR_ST_ATTENTION, st);

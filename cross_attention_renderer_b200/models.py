@@ -146,10 +146,21 @@ class CrossAttentionRenderer(nn.Module):
         return self._wcache[1]
 
     def _packed_features(self, z, bf16):
-        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in z) + (bf16,)
-        if self._fcache is None or self._fcache[0] != key:
-            self._fcache = (key, packing.pack_features([t.detach().float() for t in z], bf16))
+        # The cache entry keeps the SOURCE tensors alive: a key made of (data_ptr, _version, shape) alone
+        # would match a different scene's maps that the caching allocator placed at the recycled addresses
+        # of freed ones (same shapes, _version 0), and the previous scene's packed features would be
+        # rendered silently.  `is` on the held tensors cannot alias.
+        c = self._fcache
+        if (c is not None and c[0] == bf16 and len(c[2]) == len(z) and all(a is t_ for a, t_ in zip(c[2], z))
+                and c[3] == tuple(t._version for t in z)):
+            return c[1]
+        self._fcache = (bf16, packing.pack_features([t.detach().float() for t in z], bf16), list(z),
+                        tuple(t._version for t in z))
         return self._fcache[1]
+
+    def release_features(self):
+        """Drop the packed copy of the last scene batch (and the reference to its source maps)."""
+        self._fcache = None
 
     def _workspace(self, nbytes, device):
         if self._ws is None or self._ws.numel() < nbytes or self._ws.device != device:
@@ -209,10 +220,25 @@ class CrossAttentionRenderer(nn.Module):
         With autograd enabled and a weight or feature map that requires grad, the call goes
         through ``_RenderFunction`` (training-mode forward + ``car_render_backward``): ``rgb``
         and ``depth_ray`` are then differentiable like the reference's (training.py:92,125)."""
-        needs_grad = torch.is_grad_enabled() and debug_taps is None and (
+        # The differentiable path is the TRAINING path: it runs the exact-fp32 unfused kernels on the
+        # whole ray range as one chunk with every activation resident (training.py:92 calls the module in
+        # train mode on 192 rays per scene).  It is therefore gated on ``self.training``: a module in
+        # eval() mode always runs the configured inference precision, grad mode or not, and its outputs
+        # carry no grad_fn (like calling the reference under torch.no_grad(), eval_realestate10k.py:38).
+        needs_grad = self.training and torch.is_grad_enabled() and debug_taps is None and (
             any(t.requires_grad for t in z)
             or any(p.requires_grad for n, p in self.named_parameters() if n in HOT_PATH_PARAMS))
         if needs_grad:
+            rays = (b * R) if ray_range is None else (ray_range[1] - ray_range[0])
+            need = _lib.load().car_train_workspace_bytes(_lib.PREC_FP32_SIMT, self.npoints, max(1, rays))
+            free = torch.cuda.mem_get_info(z[0].device)[0] + torch.cuda.memory_reserved(z[0].device) \
+                - torch.cuda.memory_allocated(z[0].device)
+            if need > free:
+                raise RuntimeError(
+                    f"training-mode forward over {rays} rays x {self.npoints} samples keeps {need / 2**30:.1f} GiB of "
+                    f"activations for backward ({free / 2**30:.1f} GiB free): render fewer rays per call "
+                    "(the reference trains on 192 rays per scene, train_realestate10k.py:78), or call "
+                    "model.eval() / torch.no_grad() for inference")
             params = dict(self.named_parameters())
             plist = [params[n] for n in HOT_PATH_PARAMS]
             res = _RenderFunction.apply(self, cams, uv, interval, b, R, ray_range, z[0], z[1], z[2], *plist)
@@ -248,10 +274,12 @@ class CrossAttentionRenderer(nn.Module):
         if train:
             # the activations stay in this buffer until backward: it belongs to the autograd node
             ws = torch.empty(lib.car_train_workspace_bytes(prec, P, max(1, g1 - g0)), dtype=torch.uint8, device=dev)
+            chunk_arg = 0
         else:
             chunk = self.chunk_rays or lib.car_default_chunk_rays(prec, P, use_fused)
             chunk = max(1, min(chunk, g1 - g0))
             ws = self._workspace(lib.car_workspace_bytes(prec, P, chunk, use_fused), dev)
+            chunk_arg = chunk
         out = {
             "rgb": torch.zeros(b, 1, R, 3, device=dev),
             "valid_mask": torch.zeros(b, R, 1, device=dev),
@@ -293,6 +321,7 @@ class CrossAttentionRenderer(nn.Module):
         a.stream = torch.cuda.current_stream(dev).cuda_stream
         a.use_fused = use_fused
         a.train = int(train)
+        a.chunk_rays = chunk_arg
         with torch.cuda.device(dev):
             _lib.check(lib.car_render_forward(a), "car_render_forward")
         self.last_launch_count = lib.car_last_launch_count()

@@ -67,6 +67,8 @@ def base_parser(description, train=False):
     p.add_argument("--precision", type=str, default="fp32", choices=["fp32", "bf16", "fp32_simt"])
     p.add_argument("--encoder_module", type=str, default=None,
                    help="'pkg.mod:factory' returning the reference encoder module; default: stand-in encoder")
+    p.add_argument("--allow_encoder_mismatch", action="store_true", default=False,
+                   help="load a checkpoint whose encoder.* tensors do not match this model's encoder (renderer weights only)")
     p.add_argument("--max_steps", type=int, default=None, help="stop after this many iterations / scenes")
     p.add_argument("--master_port", type=int, default=1493 if train else 1492)
     return p
@@ -87,12 +89,26 @@ def build_model(opt, device):
     return model.to(device)
 
 
-def load_checkpoint(model, path, optimizer=None):
+def load_checkpoint(model, path, optimizer=None, allow_encoder_mismatch=False):
     """Reference file format: ``{'model': state_dict, 'optimizer': state_dict}``, loaded with
     ``strict=False``; the optimizer state is NOT restored (train_realestate10k.py:95-106)."""
     print(f"Loading weights from {path}...")
     sd = torch.load(path, map_location="cpu")
     missing, unexpected = model.load_state_dict(sd["model"], strict=False)
+    # strict=False hides mismatches: say what was not loaded.  Renderer layers the n_view=2 forward never
+    # touches (latent_avg_*, update_val_merge) are expected to be fine either way; encoder weights are not.
+    enc_unexpected = [k for k in unexpected if k.startswith("encoder.")]
+    enc_missing = [k for k in missing if k.startswith("encoder.")]
+    if unexpected:
+        print(f"  checkpoint keys NOT used by this model ({len(unexpected)}): {list(unexpected)[:6]}{' ...' if len(unexpected) > 6 else ''}")
+    if missing:
+        print(f"  model parameters NOT in the checkpoint ({len(missing)}): {list(missing)[:6]}{' ...' if len(missing) > 6 else ''}")
+    if (enc_unexpected or enc_missing) and not allow_encoder_mismatch:
+        raise RuntimeError(
+            f"{len(enc_unexpected)} encoder.* tensors of the checkpoint do not fit this model's encoder and "
+            f"{len(enc_missing)} encoder parameters stay at their initial values: the renderer would run on "
+            "features the checkpoint was not trained with.  Pass --encoder_module <pkg.mod:factory> for the "
+            "encoder the checkpoint was trained with, or --allow_encoder_mismatch to load the renderer weights only.")
     return missing, unexpected
 
 

@@ -44,7 +44,7 @@ def render(gpu, opt):
     dev = C.init_distributed(gpu, opt.gpus, opt.master_port)
     model = C.build_model(opt, dev)
     if opt.checkpoint_path is not None:
-        C.load_checkpoint(model, opt.checkpoint_path)
+        C.load_checkpoint(model, opt.checkpoint_path, allow_encoder_mismatch=opt.allow_encoder_mismatch)
     model = model.eval()
     model.pixel_val_to_cpu = False
     if not opt.synthetic:

@@ -26,7 +26,7 @@ def multigpu_train(gpu, opt):
     model = C.build_model(opt, dev)
     optimizer = torch.optim.Adam(lr=opt.lr, params=model.parameters(), betas=(0.99, 0.999))
     if opt.checkpoint_path is not None:
-        C.load_checkpoint(model, opt.checkpoint_path)
+        C.load_checkpoint(model, opt.checkpoint_path, allow_encoder_mismatch=opt.allow_encoder_mismatch)
     if opt.gpus > 1:
         C.sync_model(model)
     model.train()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CAR_ABI_VERSION 6
+#define CAR_ABI_VERSION 7
 
 /* Arithmetic of the per-sample MLP GEMMs (everything else is fp32/fp64). */
 enum car_precision {
@@ -150,6 +150,9 @@ typedef struct car_render_args {
                                      ray range is processed as one chunk on the unfused fp32 path and
                                      every activation stays in `workspace` (>= car_train_workspace_bytes)
                                      for car_render_backward.  Needs CAR_PREC_FP32_SIMT, fp32 maps.  */
+  int32_t chunk_rays;             /* rays per workspace chunk; 0 = car_default_chunk_rays().  The library
+                                     uses exactly this chunk (clipped to the ray range) and fails with -8
+                                     if `workspace_bytes` < car_workspace_bytes(precision, P, chunk, use_fused) */
 } car_render_args;
 
 /* Rays are processed in chunks of `chunk_rays`; workspace scales with the chunk. */
@@ -225,16 +228,6 @@ int car_gemm_umma_test(const uint16_t *a_hi, const uint16_t *a_lo, const uint16_
 /* Diagnostics: device buffer of 32 uint64 that the fused kernel fills with per-role barrier-wait
  * cycle counts of pair 0 (layout documented in car_fused.cu); NULL disables. */
 int car_debug_set_fused_stats(void *dev_u64x32);
-
-/* Micro-benchmark: cycles for iters*nops back-to-back tcgen05.mma (M x N x 16, bf16) from resident smem. */
-int car_mma_rate_test(int cg, int M, int N, int sw, int iters, int nops, int ctas, void *out_u64, void *stream);
-
-/* CTA-pair (cta_group::2) tcgen05 GEMM, the building block of the fused per-ray kernel, exported
- * for tests: C[M][N] = A·W^T (+bias); N is processed as `nch` MMA chunks; `dump` (optional)
- * receives the raw TMEM image [pairs*2][128 lanes][N/2] of each pair's first tile. */
-int car_gemm_pair_test(const uint16_t *a_hi, const uint16_t *a_lo, const uint16_t *w_hi,
-                       const uint16_t *w_lo, const float *bias, float *c, float *dump, int M, int N,
-                       int K, int nch, int split3, int relu, int max_pairs, int bk /*32|64*/, void *stream);
 
 #ifdef __cplusplus
 }

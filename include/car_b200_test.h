@@ -1,0 +1,29 @@
+/*
+ * car_b200_test.h - entry points of libcar_b200_test.so: micro-benchmarks and building-block test
+ * kernels used while sizing the fused per-ray kernel (scripts/mma_rate.py, tests/test_gpu_gemm.py).
+ * They are NOT part of the product library (libcar_b200.so, include/car_b200.h) and replace nothing
+ * in the reference.
+ */
+#ifndef CAR_B200_TEST_H
+#define CAR_B200_TEST_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Micro-benchmark: cycles for iters*nops back-to-back tcgen05.mma (M x N x 16, bf16) from resident smem. */
+int car_mma_rate_test(int cg, int M, int N, int sw, int iters, int nops, int ctas, void *out_u64, void *stream);
+
+/* CTA-pair (cta_group::2) tcgen05 GEMM, the building block of the fused per-ray kernel, exported
+ * for tests: C[M][N] = A·W^T (+bias); N is processed as `nch` MMA chunks; `dump` (optional)
+ * receives the raw TMEM image [pairs*2][128 lanes][N/2] of each pair's first tile. */
+int car_gemm_pair_test(const uint16_t *a_hi, const uint16_t *a_lo, const uint16_t *w_hi,
+                       const uint16_t *w_lo, const float *bias, float *c, float *dump, int M, int N,
+                       int K, int nch, int split3, int relu, int max_pairs, int bk /*32|64*/, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAR_B200_TEST_H */

@@ -2,7 +2,7 @@ import sys, os
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 import torch
 from cross_attention_renderer_b200 import _lib
-lib = _lib.load()
+lib = _lib.load_test()
 st = torch.cuda.current_stream().cuda_stream
 out = torch.zeros(4, dtype=torch.int64, device="cuda")
 iters = 2000

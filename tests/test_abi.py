@@ -29,6 +29,14 @@ def test_header_symbols_exported(lib):
     assert declared == set(_lib.SYMBOLS), (declared ^ set(_lib.SYMBOLS))
     for name in declared:
         assert hasattr(lib, name), name
+    # the micro-benchmark / building-block kernels live in their own library and header
+    tsrc = open(os.path.join(REPO, "include", "car_b200_test.h")).read()
+    tdecl = set(re.findall(r"\b(car_[a-z0-9_]+)\s*\(", tsrc))
+    assert tdecl == set(_lib.TEST_SYMBOLS), (tdecl ^ set(_lib.TEST_SYMBOLS))
+    tlib = _lib.load_test()
+    for name in tdecl:
+        assert hasattr(tlib, name), name
+        assert not hasattr(lib, name), f"{name} must not be exported by the product library"
 
 
 def test_version(lib):
@@ -45,9 +53,9 @@ def test_struct_layout_matches_c(tmp_path):
 #include <stddef.h>
 #include "car_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(car_mat), sizeof(car_weights), sizeof(car_cameras),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(car_mat), sizeof(car_weights), sizeof(car_cameras),
          sizeof(car_debug), sizeof(car_render_args), sizeof(car_weight_grads), sizeof(car_backward_args),
-         offsetof(car_render_args, train));
+         offsetof(car_render_args, train), offsetof(car_render_args, chunk_rays));
   printf("%zu %zu %zu %zu\\n", offsetof(car_backward_args, fwd), offsetof(car_backward_args, grads),
          offsetof(car_backward_args, d_feat), offsetof(car_backward_args, stream));
   printf("%zu %zu %zu %zu %zu %zu %zu\\n", offsetof(car_render_args, feat), offsetof(car_render_args, weights),
@@ -66,7 +74,7 @@ int main(void) {
     B = _lib.car_backward_args
     assert sizes == [C.sizeof(_lib.car_mat), C.sizeof(_lib.car_weights), C.sizeof(_lib.car_cameras),
                      C.sizeof(_lib.car_debug), C.sizeof(A), C.sizeof(_lib.car_weight_grads), C.sizeof(B),
-                     A.train.offset]
+                     A.train.offset, A.chunk_rays.offset]
     assert boffs == [B.fwd.offset, B.grads.offset, B.d_feat.offset, B.stream.offset]
     assert offs == [A.feat.offset, A.weights.offset, A.cams.offset, A.uv.offset,
                     A.workspace_bytes.offset, A.stream.offset, A.use_fused.offset]

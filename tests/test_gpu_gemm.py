@@ -62,7 +62,7 @@ def _pair_call(lib, A, W, bias, nch, split3, relu=1, max_pairs=0, dump=False, bk
 def test_pair_gemm_layout_probe():
     """D[m][n] = 256*m + n makes the TMEM image self-describing: print where rows/columns of the
     cta_group::2 accumulator live (diagnostic for the 2x2 datapath layout assumption)."""
-    lib = _lib.load()
+    lib = _lib.load_test()
     M, N, K = 128, 64, 16
     A = torch.zeros(M, K); W = torch.zeros(N, K)
     A[:, 0] = torch.arange(M).float(); A[:, 1] = 1.0
@@ -83,7 +83,7 @@ def test_pair_gemm_layout_probe():
 @pytest.mark.parametrize("split3", [0, 1])
 @pytest.mark.parametrize("bk", [64, 32])
 def test_pair_gemm(M, N, K, nch, split3, bk):
-    lib = _lib.load()
+    lib = _lib.load_test()
     g = torch.Generator().manual_seed(M * 7 + N + K)
     A = torch.randn(M, K, generator=g).cuda()
     W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
