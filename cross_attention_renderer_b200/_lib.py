@@ -113,6 +113,19 @@ def lib_path():
     return _LIB_PATH
 
 
+def build_id():
+    """Short hash of the kernel sources the library is built from: ncu summaries under profiles/ carry it,
+    and bench.py only quotes a profile's DRAM / L2 traffic for the build it is timing."""
+    import hashlib
+    csrc = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+    h = hashlib.sha256()
+    for name in sorted(os.listdir(csrc)):
+        if name.endswith((".cu", ".cuh")) or name == "Makefile":
+            h.update(name.encode())
+            h.update(open(os.path.join(csrc, name), "rb").read())
+    return h.hexdigest()[:12]
+
+
 def load():
     """dlopen the library (once) and declare prototypes.  Raises if missing."""
     global _lib

@@ -29,6 +29,30 @@ def _trans(x, y, z):
     return m
 
 
+def _rot_axis(axis, theta):
+    """Rodrigues rotation about ``axis`` (3,) by ``theta`` as a 4x4."""
+    a = axis / axis.norm().clamp_min(1e-12)
+    Kx = torch.zeros(3, 3, dtype=torch.float64)
+    Kx[0, 1], Kx[0, 2], Kx[1, 0], Kx[1, 2], Kx[2, 0], Kx[2, 1] = -a[2], a[1], a[2], -a[0], -a[1], a[0]
+    R = torch.eye(3, dtype=torch.float64) + math.sin(theta) * Kx + (1 - math.cos(theta)) * (Kx @ Kx)
+    m = torch.eye(4, dtype=torch.float64)
+    m[:3, :3] = R
+    return m
+
+
+def _look_at(pos, target):
+    """cam2world of a camera at ``pos`` whose +z axis points at ``target`` (y roughly down-world)."""
+    zax = target - pos
+    zax = zax / zax.norm()
+    up = torch.tensor([0.0, 1.0, 0.0], dtype=torch.float64)
+    xax = torch.linalg.cross(up, zax)
+    xax = xax / xax.norm()
+    yax = torch.linalg.cross(zax, xax)
+    m = torch.eye(4, dtype=torch.float64)
+    m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = xax, yax, zax, pos
+    return m
+
+
 def make_intrinsics(H):
     """Pinhole f=225 px at 256² (reference dataset/load_video_superglue.py:465)."""
     k = torch.eye(4, dtype=torch.float32)
@@ -48,7 +72,13 @@ def make_inputs(b, H, Ht=None, Wt=None, seed=0, mode="default", rays=None, n_ctx
     """Build the reference-style ``input`` dict for ``b`` scenes, ``n_ctx`` context views (2 unless
     stated; 1 keeps the first camera of the pair, 3 adds one below the baseline).
 
-    mode: "default"  wide-baseline converging pair, query between them;
+    mode: "sweep"    bit-exactness sweep: per scene a random query pose (rotation up to
+                     ~0.6 rad about a random axis, translation N(0, 0.5)), and every scene with s % 6 != 0 one
+                     degenerate configuration: 1 the central target ray passes through context camera 0's
+                     centre, 2 the query looks along context 0's x axis (central ray parallel to its image
+                     plane), 3 the query sits behind context camera 0 looking forward, 4 query at the context
+                     camera, 5 query far outside both frusta;
+          "default"  wide-baseline converging pair, query between them;
           "outside"  query far outside both frusta looking away (white rays,
                      all-invalid tie-break of epipolar.py:142);
           "mixed"    per-scene alternation of the two plus a query that sits
@@ -70,7 +100,20 @@ def make_inputs(b, H, Ht=None, Wt=None, seed=0, mode="default", rays=None, n_ctx
         m = mode
         if mode == "mixed":
             m = ("default", "outside", "at_camera")[s % 3]
-        if m == "default":
+        if mode == "sweep":
+            m = ("random", "through_centre", "parallel", "behind", "at_camera", "outside")[s % 6]
+        if m == "random":
+            ax = torch.randn(3, generator=g, dtype=torch.float64)
+            q = _trans(*(torch.randn(3, generator=g, dtype=torch.float64) * 0.5).tolist()) @ _rot_axis(ax, 0.6 * float(torch.rand(1, generator=g, dtype=torch.float64)))
+        elif m == "through_centre":
+            # query placed in front of context camera 0, looking straight at its centre
+            pos = c0 @ torch.tensor([0.4, -0.2, 1.5, 1.0], dtype=torch.float64)
+            q = _look_at(pos[:3], c0[:3, 3])
+        elif m == "parallel":
+            q = c0.clone() @ _trans(0.0, 0.0, 1.0) @ _rot_y(math.pi / 2)
+        elif m == "behind":
+            q = c0.clone() @ _trans(0.05, -0.03, -1.0)
+        elif m == "default":
             q = _trans(0.05 * (s % 5) - 0.1, 0.02 * (s % 3), 0.03 * (s % 2))
         elif m == "outside":
             q = _trans(5.0, 0.3, -2.0) @ _rot_y(2.6)

@@ -19,7 +19,7 @@ def test_reference_arm_json_line():
     assert d["impl"] == "reference" and d["unit"] == "rays/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] >= 3
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "rays" in cb["sample"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "rays" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["vs_baseline"] is None and d["data"] == "synthetic" and "workload" in d["config"]
 
