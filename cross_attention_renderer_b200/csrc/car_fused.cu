@@ -19,7 +19,14 @@
 //
 // TMEM (per CTA, 64 rows in the "2x2" layout => N/2 columns): acc1 288 + acc3 208 = 496 <= 512.
 // SMEM: X ring + H ring (A operands), B ring (W1 / F slices via TMA, each CTA loads its half of
-// every N chunk), tap table.  All operand tiles are K-major, 64-byte swizzle, 32 K per stage.
+// every N chunk), tap table.  All operand tiles are K-major and swizzled; KS K-columns per stage:
+//   KS = 32 (64-byte swizzle rows)  hi+lo mode (CAR_PREC_FP32_3XBF16): 8 KB A stages, 36 KB B stages
+//   KS = 64 (128-byte swizzle rows) bf16 mode: half as many stages per ray.  The MMA-issuing thread pays
+//           ~400 cycles per stage whatever the stage holds (barrier waits, fence, election, descriptor
+//           set-up, commits: scripts/fused_stalls.py; a second issuing warp did not help, profiles/README.md),
+//           against 200-290 cycles of tensor time per 32-wide stage in bf16 - so the stages are made wider.
+//           The H ring then pairs the two lane halves of one accumulator block in one stage, and F is read
+//           through a column-permuted copy (car_weights::kv_fold64) whose K order is the epilogue's.
 #include <math.h>
 #include <stdlib.h>
 
@@ -33,14 +40,11 @@ int make_tmap_bf16(CUtensorMap *tm, const uint16_t *base, int rows, int K, int l
 namespace {
 using namespace ptx;
 
-constexpr int KS = 32;                 // K per stage (bf16 elements) = one 64-byte swizzle row
 constexpr int ROWS = 64;               // sample rows per CTA
-constexpr int NXMAX = 8;               // X ring depth is Cfg::NX (6 for the hi+lo mode, 8 for bf16)
-constexpr int NHMAX = 4;               // H ring depth
+constexpr int NXMAX = 8;               // X ring depth is Cfg::NX
+constexpr int NHMAX = 6;               // H ring depth is Cfg::NH (the ring doubles as the 24 KB / 32 KB acc3 staging area)
 constexpr int N1 = 576, N1CH = 192, N1C = 3;      // GEMM1: 3 MMA chunks of 192
 constexpr int N3 = 416, N3CH = 208, N3C = 2;      // GEMM3: 2 MMA chunks of 208
-constexpr int K1_STAGES = 19;          // ceil(592 / 32); the last stage holds 16 valid columns
-constexpr int K3_STAGES = 18;          // 576 / 32
 constexpr int ACC1_COL = 0, ACC3_COL = 288;
 constexpr int PRODUCER_WARPS = 8;
 constexpr int THREADS = (2 + 4 + PRODUCER_WARPS) * 32;   // 448
@@ -76,16 +80,25 @@ struct FusedParams {
   unsigned long long *stats;           // optional [32] stall counters (see timed_wait), else null
 };
 
-template <int SPLIT> struct Cfg {
+template <int SPLIT, int KS_> struct Cfg {
+  static constexpr int KS = KS_;                                   // K per stage (bf16 elements)
+  static constexpr int SW = KS * 2;                                // swizzle row bytes: 64 or 128
+  static constexpr int KSTEPS = KS / 16;                           // UMMA K = 16 per instruction
+  static constexpr int K1_STAGES = (CAR_K_ENC + KS - 1) / KS;      // 19 / 10; the last stage holds 16 valid columns
+  static constexpr int K3_STAGES = N1 / KS;                        // 18 / 9
   static constexpr int OPS = SPLIT == 3 ? 2 : 1;                  // hi (+lo) copies
-  static constexpr int A_HALF = ROWS * KS * 2;                     // 4096 B (hi part of an A stage)
+  static constexpr int A_HALF = ROWS * SW;                         // 4096 / 8192 B (hi part of an A stage)
   static constexpr int A_STAGE = A_HALF * OPS;
-  static constexpr int W1_CHUNK = (N1CH / 2) * KS * 2;             // 6144 B
-  static constexpr int F_CHUNK = (N3CH / 2) * KS * 2;              // 6656 B
-  static constexpr int B_HALF = N1C * W1_CHUNK;                    // 18432 B (>= N3C*F_CHUNK = 13312)
+  static constexpr int W1_CHUNK = (N1CH / 2) * SW;                 // 6144 / 12288 B
+  static constexpr int F_CHUNK = (N3CH / 2) * SW;                  // 6656 / 13312 B
+  static constexpr int B_HALF = N1C * W1_CHUNK;                    // 18432 / 36864 B (>= N3C*F_CHUNK)
   static constexpr int B_STAGE = B_HALF * OPS;
-  static constexpr int NH = 4;
-  static constexpr int NX = SPLIT == 3 ? 6 : 8;
+  static constexpr int NH = KS == 64 ? 3 : (SPLIT == 3 ? 4 : 6);   // NH * A_STAGE >= 24 KB (32 KB with lo copies): acc3 staging
+  static constexpr int NX = KS == 64 ? 6 : (SPLIT == 3 ? 6 : 8);
+  static constexpr int H_ARRIVALS = KS == 64 ? 8 : 4;              // epilogue warps per H stage (x 2 CTAs)
+  static_assert(SW == 64 || SW == 128, "KS must be 32 or 64");
+  static_assert(NH * A_STAGE >= (SPLIT == 3 ? 32768 : 24576), "H ring too small to stage acc3");
+  static_assert(W1_CHUNK % 1024 == 0 || SW == 64, "128-byte-swizzled chunks must start on 1 KB boundaries");
 };
 
 __device__ __forceinline__ float downgrade(float x) {
@@ -131,12 +144,13 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t 
   }
 }
 
-template <int SPLIT, typename FT>
+template <int SPLIT, typename FT, int KS>
 __global__ void __launch_bounds__(THREADS, 1)
 k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_constant__ CUtensorMap tm_w1_lo,
                const __grid_constant__ CUtensorMap tm_f_hi, const __grid_constant__ CUtensorMap tm_f_lo,
                FusedParams p) {
-  using C = Cfg<SPLIT>;
+  using C = Cfg<SPLIT, KS>;
+  constexpr int SW = C::SW, K1_STAGES = C::K1_STAGES, K3_STAGES = C::K3_STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *xs = smem;                                       // NX x A_STAGE
@@ -189,7 +203,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
     prefetch_tmap(&tm_w1_hi);
     prefetch_tmap(&tm_f_hi);
     for (int s = 0; s < NX; ++s) { mbar_init(&x_full[s], 4);   /* 2 warps of the owning group x 2 CTAs */ mbar_init(&x_empty[s], 1); }
-    for (int s = 0; s < NH; ++s) { mbar_init(&h_full[s], 4); mbar_init(&h_empty[s], 1); }
+    for (int s = 0; s < NH; ++s) { mbar_init(&h_full[s], C::H_ARRIVALS); mbar_init(&h_empty[s], 1); }
     for (int s = 0; s < p.nb; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], p.cl / 2); }
     mbar_init(a1_full, 1); mbar_init(a1_empty, 8);
     mbar_init(a3_full, 1); mbar_init(a3_empty, 8);
@@ -226,8 +240,13 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
             const int s = bq % p.nb;
             timed_wait(&b_empty[s], ((bq / p.nb) & 1) ^ 1, st, 0);
             uint8_t *st = bs + (size_t)s * C::B_STAGE;
-            const int half = q & 1, cj = q >> 1, c = cj / 3, jj = cj - c * 3;
-            const int k0 = v * N1 + c * N1CH + half * (N1CH / 2) + jj * KS;
+            int k0;
+            if (KS == 32) {                                                     // the epilogue's production order
+              const int half = q & 1, cj = q >> 1, c = cj / 3, jj = cj - c * 3;
+              k0 = v * N1 + c * N1CH + half * (N1CH / 2) + jj * KS;
+            } else {
+              k0 = v * N1 + q * KS;                                             // kv_fold64 is stored in that order
+            }
             if (leader) mbar_expect_tx(&b_full[s], (uint32_t)(N3C * C::F_CHUNK * C::OPS * 2));
             for (int e = 0; e < N3C; ++e) {
               const int n0 = e * N3CH + (int)rank * (N3CH / 2);
@@ -261,12 +280,12 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
             timed_wait(&b_full[sb], pb, st, 2);
             tc_fence_after();
             if (elect_one()) {
-              const uint64_t da = make_desc<64>(smem_u32(xs + (size_t)sx * C::A_STAGE));
-              const uint64_t db = make_desc<64>(smem_u32(bs + (size_t)sb * C::B_STAGE));
+              const uint64_t da = make_desc<SW>(smem_u32(xs + (size_t)sx * C::A_STAGE));
+              const uint64_t db = make_desc<SW>(smem_u32(bs + (size_t)sb * C::B_STAGE));
               const uint32_t d0 = tmem_base + ACC1_COL;
 #pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                if (k == 1 && kb == K1_STAGES - 1) break;                   // last stage: 16 valid K columns
+              for (int k = 0; k < C::KSTEPS; ++k) {
+                if (k >= 1 && kb == K1_STAGES - 1) break;                   // last stage: 16 valid K columns
                 const uint32_t acc = (kb | k) ? 1u : 0u;
 #pragma unroll
                 for (int c = 0; c < N1C; ++c) {
@@ -293,11 +312,11 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
             timed_wait(&b_full[sb], pb, st, 5);
             tc_fence_after();
             if (elect_one()) {
-              const uint64_t da = make_desc<64>(smem_u32(hs + (size_t)sh * C::A_STAGE));
-              const uint64_t db = make_desc<64>(smem_u32(bs + (size_t)sb * C::B_STAGE));
+              const uint64_t da = make_desc<SW>(smem_u32(hs + (size_t)sh * C::A_STAGE));
+              const uint64_t db = make_desc<SW>(smem_u32(bs + (size_t)sb * C::B_STAGE));
               const uint32_t d0 = tmem_base + ACC3_COL;
 #pragma unroll
-              for (int k = 0; k < 2; ++k) {
+              for (int k = 0; k < C::KSTEPS; ++k) {
                 const uint32_t acc = (v | q | k) ? 1u : 0u;
 #pragma unroll
                 for (int e = 0; e < N3C; ++e) {
@@ -342,12 +361,14 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
           tmem_ld_wait();                                                      // r[cj & 1] has landed
           if (cj + 1 < 9) {                                                    // next chunk overlaps this one's math
             const int c2 = (cj + 1) / 3, j2 = (cj + 1) - c2 * 3;
-            tmem_ld32(tlane + ACC1_COL + (uint32_t)(c2 * (N1CH / 2) + j2 * KS), r[(cj + 1) & 1]);
+            tmem_ld32(tlane + ACC1_COL + (uint32_t)(c2 * (N1CH / 2) + j2 * 32), r[(cj + 1) & 1]);
           }
           long long tc0 = st ? clock64() : 0;
-          const uint32_t hq = (hi_count + cj) * 2 + (uint32_t)half;            // global H chunk index
+          // KS = 32: one H stage per (block, lane half); KS = 64: the two lane halves of a block share a stage,
+          // half h filling the K columns [32 h, 32 h + 32)
+          const uint32_t hq = KS == 32 ? (hi_count + cj) * 2 + (uint32_t)half : hi_count + cj;   // global H stage index
           const int sh = hq % NH;
-          const int n0 = c * N1CH + half * (N1CH / 2) + jj * KS;
+          const int n0 = c * N1CH + half * (N1CH / 2) + jj * 32;
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -361,7 +382,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
           uint8_t *dst = hs + (size_t)sh * C::A_STAGE;
 #pragma unroll
           for (int c16 = 0; c16 < 4; ++c16) {
-            const uint32_t off = swz_offset<64>(row, c16);
+            const uint32_t off = swz_offset<SW>(row, (KS == 64 ? half * 4 : 0) + c16);
             *reinterpret_cast<uint4 *>(dst + off) = make_uint4(hi[4 * c16], hi[4 * c16 + 1], hi[4 * c16 + 2], hi[4 * c16 + 3]);
             if (SPLIT == 3) *reinterpret_cast<uint4 *>(dst + C::A_HALF + off) = make_uint4(lo[4 * c16], lo[4 * c16 + 1], lo[4 * c16 + 2], lo[4 * c16 + 3]);
           }
@@ -378,54 +399,117 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
         if (lane == 0) mbar_arrive_cluster(a1_empty, leader_crank);
       }
       // ---- acc3 -> V (fp32) and relu(key pre-activation) (bf16 hi/lo) ----
+      // Staged through shared memory and written out row-contiguously: a direct store of the TMEM image
+      // (lane = row, 1152-byte row pitch) touches 32 different lines per instruction - 6.6 k L1 wavefronts per ray,
+      // more than the whole bilinear gather - and kept the epilogue warps busy for 16-23 k cycles per ray
+      // (profiles/r02_fused_stalls.txt).  The staging area is the H ring: it is idle from a3_full (every GEMM3 MMA
+      // of this ray has retired) until these same warps drain the next ray's acc1.
+      //   rounds 0..2: V columns [96 r, 96 r + 96) as three [64 rows x 32 fp32] boxes (128-byte swizzle)
+      //   round  3   : relu(key) as two [64 x 64 bf16] boxes (hi) [+ two (lo)]
+      // Accumulator column n of the pair tile lives at chunk e = n / 208, lane half (n % 208) / 104.
       timed_wait(a3_full, rq & 1, st, 2);
       tc_fence_after();
       const long long td0 = st ? clock64() : 0;
-      const size_t grow = row_base(ray) + row;
-      // per lane: 104 accumulator columns per MMA chunk = 3 x 32 + 8; 32 fp32 = one 128-byte line
-      auto emit = [&](const uint32_t *r, int n0, int cnt) {                // cnt = 32 or 8 columns from n0
+      const int grow0 = (int)row_base(ray);
+      const uint32_t tc0_ = tlane + ACC3_COL, tc1_ = tlane + ACC3_COL + (uint32_t)(N3CH / 2);
+      // V columns [n0, n0 + CNT) from TMEM columns [tcol, tcol + CNT) of this lane -> staging box of round n0 / 96
+      auto stage_v = [&](uint32_t tcol, int n0, auto CNT_) {
+        constexpr int CNT = decltype(CNT_)::value;
+        uint32_t r[CNT];
+        if constexpr (CNT == 32) tmem_ld32(tcol, r);
+        else if constexpr (CNT == 16) tmem_ld16(tcol, r);
+        else tmem_ld8(tcol, r);
+        tmem_ld_wait();
 #pragma unroll
-        for (int i0 = 0; i0 < 32; i0 += 8) {
-          if (i0 >= cnt) break;
-          const int n = n0 + i0;
-          float vv[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) vv[i] = __uint_as_float(r[i0 + i]) + sbiasf[n + i];
-          if (!valid) continue;
-          if (n < CAR_C_LAT) {
-            float *o = p.value + grow * CAR_C_LAT + n;
-            *reinterpret_cast<float4 *>(o) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-            *reinterpret_cast<float4 *>(o + 4) = make_float4(vv[4], vv[5], vv[6], vv[7]);
-          } else {
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) split2<SPLIT == 3>(fmaxf(vv[2 * i], 0.f), fmaxf(vv[2 * i + 1], 0.f), hi[i], lo[i]);
-            const size_t o = grow * 128 + (n - CAR_C_LAT);
-            *reinterpret_cast<uint4 *>(p.kh_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            if (SPLIT == 3) *reinterpret_cast<uint4 *>(p.kh_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          }
+        for (int i = 0; i < CNT; i += 4) {
+          const int n = n0 + i, rel = n % 96;
+          const float4 bb = *reinterpret_cast<const float4 *>(sbiasf + n);
+          const float4 o = make_float4(__uint_as_float(r[i]) + bb.x, __uint_as_float(r[i + 1]) + bb.y,
+                                       __uint_as_float(r[i + 2]) + bb.z, __uint_as_float(r[i + 3]) + bb.w);
+          *reinterpret_cast<float4 *>(hs + (rel >> 5) * 8192 + swz_offset<128>(row, (rel & 31) >> 2)) = o;
         }
       };
+      // relu(key) columns [k0, k0 + CNT) (accumulator columns 288 + k) -> bf16 hi (+lo) staging boxes
+      auto stage_k = [&](uint32_t tcol, int k0, auto CNT_) {
+        constexpr int CNT = decltype(CNT_)::value;
+        uint32_t r[CNT];
+        if constexpr (CNT == 32) tmem_ld32(tcol, r);
+        else if constexpr (CNT == 16) tmem_ld16(tcol, r);
+        else tmem_ld8(tcol, r);
+        tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < N3C; ++e) {
-        const uint32_t tcol = tlane + ACC3_COL + (uint32_t)(e * (N3CH / 2));
-        const int nb0 = e * N3CH + half * (N3CH / 2);
-        uint32_t ra[32], rb[32], rc[8];
-        tmem_ld32(tcol, ra);
-        tmem_ld32(tcol + 32, rb);
-        tmem_ld_wait();
-        emit(ra, nb0, 32);
-        tmem_ld32(tcol + 64, ra);
-        tmem_ld8(tcol + 96, rc);
-        emit(rb, nb0 + 32, 32);
-        tmem_ld_wait();
-        emit(ra, nb0 + 64, 32);
-        emit(rc, nb0 + 96, 8);
-      }
-      if (st) st[6] += (unsigned long long)(clock64() - td0);
+        for (int i = 0; i < CNT; i += 8) {
+          const int k = k0 + i;
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            split2<SPLIT == 3>(fmaxf(__uint_as_float(r[i + 2 * j]) + sbiasf[CAR_C_LAT + k + 2 * j], 0.f),
+                               fmaxf(__uint_as_float(r[i + 2 * j + 1]) + sbiasf[CAR_C_LAT + k + 2 * j + 1], 0.f), hi[j], lo[j]);
+          const uint32_t off = (uint32_t)((k >> 6) * 8192) + swz_offset<128>(row, (k & 63) >> 3);
+          *reinterpret_cast<uint4 *>(hs + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          if (SPLIT == 3) *reinterpret_cast<uint4 *>(hs + 16384 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      };
+      using I8 = std::integral_constant<int, 8>;
+      using I16 = std::integral_constant<int, 16>;
+      using I32 = std::integral_constant<int, 32>;
+      // staging complete -> coalesced global stores by all four warps -> staging free again.  Thread t copies the
+      // 16-byte chunk t % 8 of rows t / 8 + 16 i: one store instruction covers 4 full 128-byte lines.
+      // (TMA bulk-tensor stores from the same staging boxes were measured first: they queue behind the weight
+      // loads of the B ring in the SM's TMA unit and the per-round wait for their smem reads cost as much as the
+      // uncoalesced stores had.)
+      const int et = (int)threadIdx.x - 64;                // 0..127 among the epilogue threads
+      auto flush = [&](int round) {
+        const long long tfl0 = st ? clock64() : 0;
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (valid) {
+          const int cj = et & 7, r0 = et >> 3;
+          if (round < 3) {
+            float *vbase = p.value + (size_t)grow0 * CAR_C_LAT + round * 96 + cj * 4;
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rr = r0 + 16 * i;
+                const float4 v4 = *reinterpret_cast<const float4 *>(hs + b * 8192 + swz_offset<128>(rr, cj));
+                *reinterpret_cast<float4 *>(vbase + (size_t)rr * CAR_C_LAT + b * 32) = v4;
+              }
+          } else {
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rr = r0 + 16 * i;
+                const size_t o = ((size_t)grow0 + rr) * 128 + b * 64 + cj * 8;
+                *reinterpret_cast<uint4 *>(p.kh_hi + o) = *reinterpret_cast<const uint4 *>(hs + b * 8192 + swz_offset<128>(rr, cj));
+                if (SPLIT == 3) *reinterpret_cast<uint4 *>(p.kh_lo + o) = *reinterpret_cast<const uint4 *>(hs + 16384 + b * 8192 + swz_offset<128>(rr, cj));
+              }
+          }
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (st) st[7] += (unsigned long long)(clock64() - tfl0);
+      };
+      // round 0: V [0, 96) = columns 0..95 of chunk 0, lower lane half
+      if (half == 0) { stage_v(tc0_, 0, I32{}); stage_v(tc0_ + 32, 32, I32{}); stage_v(tc0_ + 64, 64, I32{}); }
+      flush(0);
+      // round 1: V [96, 192) = chunk 0: lower half columns 96..103, upper half columns 0..87 (n = 104 + col)
+      if (half == 0) stage_v(tc0_ + 96, 96, I8{});
+      else { stage_v(tc0_, 104, I8{}); stage_v(tc0_ + 8, 112, I16{}); stage_v(tc0_ + 24, 128, I32{}); stage_v(tc0_ + 56, 160, I32{}); }
+      flush(1);
+      // round 2: V [192, 288) = chunk 0 upper half columns 88..103 (n = 192..207), chunk 1 lower half columns 0..79 (n = 208..287)
+      if (half == 1) stage_v(tc0_ + 88, 192, I16{});
+      else { stage_v(tc1_, 208, I16{}); stage_v(tc1_ + 16, 224, I32{}); stage_v(tc1_ + 48, 256, I32{}); }
+      flush(2);
+      // round 3: relu(key): chunk 1 lower half columns 80..103 (k = 0..23), upper half columns 0..103 (k = 24..127)
+      if (half == 0) { stage_k(tc1_ + 80, 0, I8{}); stage_k(tc1_ + 88, 8, I16{}); }
+      else { stage_k(tc1_, 24, I8{}); stage_k(tc1_ + 8, 32, I32{}); stage_k(tc1_ + 40, 64, I32{}); stage_k(tc1_ + 72, 96, I32{}); }
+      // acc3 has been read completely: hand it back before the last flush
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(a3_empty, leader_crank);
+      flush(3);
+      if (st) st[6] += (unsigned long long)(clock64() - td0);
+
     }
   } else {
     // =========================== gather producers (warps 6..13) ===========================
@@ -480,76 +564,62 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
           const int h = lvl == 0 ? p.H / 4 : (lvl == 1 ? p.H / 2 : p.H);
           const int w = lvl == 0 ? p.W / 4 : (lvl == 1 ? p.W / 2 : p.W);
           const FT *img = fbase[lvl] + (size_t)(scene * 2 + v) * h * w * Cc + coff;
-          if (sizeof(FT) == 4) {
-            // 64 rows x 8 groups of 4 channels = 512 items; thread handles items gt + 64*i, i = 0..7,
-            // with a rolling window of 4 items (16 x LDG.128) in flight
-            float4 x[4][4];
-            float wt[4][4];
-            auto load_item = [&](int slot, int i) {
-              const int item = gt + 64 * i, rr = item >> 3, grp = item & 7;
-              const TapEntry t = tb[(rr * 3 + lvl) * 2 + oc];
+          // An item = one 16-byte piece of one sample row: CPI channels (4 fp32 / 8 bf16).  A stage is
+          // 64 rows x IPR items; thread gt handles items gt + 64 i, i < IPR, with a rolling window of 4 items
+          // (16 x LDG.128) in flight; the ring slot is awaited only right before the first store.
+          constexpr int CPI = sizeof(FT) == 4 ? 4 : 8;
+          constexpr int IPR = KS / CPI;                    // items per row = items per thread: 8/16 (fp32), 4/8 (bf16)
+          uint4 x[4][4];
+          float wt[4][4];
+          auto load_item = [&](int slot, int i) {
+            const int item = gt + 64 * i, rr = item / IPR, grp = item % IPR;
+            const TapEntry t = tb[(rr * 3 + lvl) * 2 + oc];
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                wt[slot][k] = t.off[k] >= 0 ? t.w[k] : 0.f;
-                const int o = t.off[k] >= 0 ? t.off[k] : 0;
-                x[slot][k] = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(img) + (size_t)o * Cc + grp * 4));
-              }
-            };
+            for (int k = 0; k < 4; ++k) {
+              wt[slot][k] = t.off[k] >= 0 ? t.w[k] : 0.f;
+              const int o = t.off[k] >= 0 ? t.off[k] : 0;
+              x[slot][k] = __ldg(reinterpret_cast<const uint4 *>(img + (size_t)o * Cc + grp * CPI));
+            }
+          };
 #pragma unroll
-            for (int i = 0; i < 4; ++i) load_item(i, i);
-            timed_wait(&x_empty[sx], xpar, st, 0);
+          for (int i = 0; i < 4; ++i) load_item(i, i);
+          timed_wait(&x_empty[sx], xpar, st, 0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int item = gt + 64 * i, rr = item >> 3, grp = item & 7, sl = i & 3;
+          for (int i = 0; i < IPR; ++i) {
+            const int item = gt + 64 * i, rr = item / IPR, grp = item % IPR, sl = i & 3;
+            if (sizeof(FT) == 4) {
               float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                acc.x = fmaf(x[sl][k].x, wt[sl][k], acc.x); acc.y = fmaf(x[sl][k].y, wt[sl][k], acc.y);
-                acc.z = fmaf(x[sl][k].z, wt[sl][k], acc.z); acc.w = fmaf(x[sl][k].w, wt[sl][k], acc.w);
+                const float ww = wt[sl][k];
+                acc.x = fmaf(__uint_as_float(x[sl][k].x), ww, acc.x); acc.y = fmaf(__uint_as_float(x[sl][k].y), ww, acc.y);
+                acc.z = fmaf(__uint_as_float(x[sl][k].z), ww, acc.z); acc.w = fmaf(__uint_as_float(x[sl][k].w), ww, acc.w);
               }
-              if (i + 4 < 8) load_item(sl, i + 4);
+              if (i + 4 < IPR) load_item(sl, i + 4);
               uint32_t h0, l0, h1, l1;
               split2<SPLIT == 3>(acc.x, acc.y, h0, l0);
               split2<SPLIT == 3>(acc.z, acc.w, h1, l1);
-              const uint32_t off = swz_offset<64>(rr, grp >> 1) + (uint32_t)((grp & 1) * 8);
+              const uint32_t off = swz_offset<SW>(rr, grp >> 1) + (uint32_t)((grp & 1) * 8);
               *reinterpret_cast<uint2 *>(dst + off) = make_uint2(h0, h1);
               if (SPLIT == 3) *reinterpret_cast<uint2 *>(dst + C::A_HALF + off) = make_uint2(l0, l1);
-            }
-          } else {
-            // bf16 maps: 64 rows x 4 groups of 8 channels = 256 items; thread handles gt + 64*i
-            uint4 x[4][4];
-            float wt[4][4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int item = gt + 64 * i, rr = item >> 2, grp = item & 3;
-              const TapEntry t = tb[(rr * 3 + lvl) * 2 + oc];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                wt[i][k] = t.off[k] >= 0 ? t.w[k] : 0.f;
-                const int o = t.off[k] >= 0 ? t.off[k] : 0;
-                x[i][k] = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint16_t *>(img) + (size_t)o * Cc + grp * 8));
-              }
-            }
-            timed_wait(&x_empty[sx], xpar, st, 0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int item = gt + 64 * i, rr = item >> 2, grp = item & 3;
+            } else {
               float a8[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) a8[j] = 0.f;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const uint32_t uu[4] = {x[i][k].x, x[i][k].y, x[i][k].z, x[i][k].w};
+                const uint32_t uu[4] = {x[sl][k].x, x[sl][k].y, x[sl][k].z, x[sl][k].w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  a8[2 * j] = fmaf(__uint_as_float(uu[j] << 16), wt[i][k], a8[2 * j]);
-                  a8[2 * j + 1] = fmaf(__uint_as_float(uu[j] & 0xffff0000u), wt[i][k], a8[2 * j + 1]);
+                  a8[2 * j] = fmaf(__uint_as_float(uu[j] << 16), wt[sl][k], a8[2 * j]);
+                  a8[2 * j + 1] = fmaf(__uint_as_float(uu[j] & 0xffff0000u), wt[sl][k], a8[2 * j + 1]);
                 }
               }
+              if (i + 4 < IPR) load_item(sl, i + 4);
               uint32_t hi[4], lo[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) split2<SPLIT == 3>(a8[2 * j], a8[2 * j + 1], hi[j], lo[j]);
-              const uint32_t off = swz_offset<64>(rr, grp);
+              const uint32_t off = swz_offset<SW>(rr, grp);
               *reinterpret_cast<uint4 *>(dst + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               if (SPLIT == 3) *reinterpret_cast<uint4 *>(dst + C::A_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
@@ -557,16 +627,17 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
         } else {
           // last stage: [tanh(pt_v / 5) (3) | zeros]; only the first 16 K-columns are multiplied
           timed_wait(&x_empty[sx], xpar, st, 0);
+          constexpr int CHK = SW / 16;                     // 16-byte chunks per row: 4 / 8
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int item = gt + 64 * i, rr = item >> 2, c16 = item & 3;
+          for (int i = 0; i < CHK; ++i) {
+            const int item = gt + 64 * i, rr = item / CHK, c16 = item % CHK;
             uint32_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
             if (c16 == 0) {
               const float *T = th + rr * 8 + v * 4;
               split2<SPLIT == 3>(T[0], T[1], hi[0], lo[0]);
               split2<SPLIT == 3>(T[2], 0.f, hi[1], lo[1]);
             }
-            const uint32_t off = swz_offset<64>(rr, c16);
+            const uint32_t off = swz_offset<SW>(rr, c16);
             *reinterpret_cast<uint4 *>(dst + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             if (SPLIT == 3) *reinterpret_cast<uint4 *>(dst + C::A_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
@@ -582,7 +653,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
   if (st && lane == 0) {
     const unsigned long long tot = (unsigned long long)(clock64() - t_begin);
     if (warp == 1) { for (int i = 0; i < 6; ++i) atomicAdd(p.stats + i, st[i]); atomicAdd(p.stats + 6, tot); }
-    else if (warp == 2) { for (int i = 0; i < 7; ++i) atomicAdd(p.stats + 8 + i, st[i]); atomicAdd(p.stats + 15, tot); }
+    else if (warp == 2) { for (int i = 0; i < 7; ++i) atomicAdd(p.stats + 8 + i, st[i]); atomicAdd(p.stats + 15, tot); atomicAdd(p.stats + 22, st[7]); }
     else if (warp == 6) { atomicAdd(p.stats + 16, st[0]); atomicAdd(p.stats + 17, tot); atomicAdd(p.stats + 18, st[2]); atomicAdd(p.stats + 19, st[3]); }
     else if (warp == 0) { atomicAdd(p.stats + 20, st[0]); atomicAdd(p.stats + 21, tot); }
   }
@@ -603,7 +674,12 @@ unsigned long long *g_fused_stats = nullptr;   // device buffer [32], set by car
 int launch_fused_encode(const car_render_args &a, int g0, int g1, const float *geom, float *value,
                         uint16_t *kh_hi, uint16_t *kh_lo, cudaStream_t st) {
   const int split3 = a.precision == CAR_PREC_FP32_3XBF16;
-  const car_mat &W1 = a.weights.enc1, &F = a.weights.kv_fold;
+  // stage width: 64 K-columns in bf16 mode (needs the column-permuted F), 32 in the hi+lo mode.  CAR_KS=32 forces
+  // the narrow stages (A/B diagnostics).
+  static int ks_env = -1;
+  if (ks_env < 0) { const char *e_ = getenv("CAR_KS"); ks_env = e_ ? atoi(e_) : 0; }
+  const int KS = (!split3 && ks_env != 32 && a.weights.kv_fold64.hi) ? 64 : 32;
+  const car_mat &W1 = a.weights.enc1, &F = KS == 64 ? a.weights.kv_fold64 : a.weights.kv_fold;
   if (a.P % ROWS != 0 || a.P > 256 || !F.hi || F.N != N3 || F.K != 2 * N1 || W1.N != N1 || W1.K != CAR_K_ENC) {
     set_error("fused encode: unsupported configuration (P=%d)", a.P);
     return -20;
@@ -623,11 +699,13 @@ int launch_fused_encode(const car_render_args &a, int g0, int g1, const float *g
   p.geom = geom; p.bias1 = W1.bias; p.biasf = F.bias;
   p.value = value; p.kh_hi = kh_hi; p.kh_lo = kh_lo;
   p.stats = g_fused_stats;
-  const int a_stage = ROWS * KS * 2 * (split3 ? 2 : 1);
-  const int b_stage = N1C * (N1CH / 2) * KS * 2 * (split3 ? 2 : 1);
-  const int nh = 4, nx = split3 ? 6 : 8;
+  const int ops = split3 ? 2 : 1;
+  const int a_stage = ROWS * KS * 2 * ops;
+  const int b_stage = N1C * (N1CH / 2) * KS * 2 * ops;
+  const int nh = KS == 64 ? Cfg<1, 64>::NH : (split3 ? Cfg<3, 32>::NH : Cfg<1, 32>::NH);
+  const int nx = KS == 64 ? Cfg<1, 64>::NX : (split3 ? Cfg<3, 32>::NX : Cfg<1, 32>::NX);
   const size_t fixed = (size_t)(nx + nh) * a_stage + 2 * (ROWS * 3 * 2 * sizeof(TapEntry) + ROWS * 8 * 4) + (N1 + N3) * 4 +
-                       (2 * NXMAX + 2 * NHMAX + 2 * MAXB + 4) * 8 + 16 + 512;
+                       (2 * NXMAX + 2 * NHMAX + 2 * MAXB + 4) * 8 + 16 + 1024;
   int nb = (int)((227 * 1024 - fixed) / b_stage);
   if (nb > MAXB) nb = MAXB;
   if (nb < 2) { set_error("fused encode: not enough shared memory"); return -21; }
@@ -642,9 +720,9 @@ int launch_fused_encode(const car_render_args &a, int g0, int g1, const float *g
   if (p.cl == 4) { pairs &= ~1; if (pairs < 2) { p.cl = 2; pairs = (g1 - g0) * p.hpr < sms / 2 ? (g1 - g0) * p.hpr : sms / 2; } }
   cudaError_t e = cudaSuccess;
   prof_pre(CAR_ST_FUSED, st);
-#define CAR_LAUNCH(S, T)                                                                                    \
+#define CAR_LAUNCH(S, T, K)                                                                                 \
   do {                                                                                                      \
-    e = cudaFuncSetAttribute(k_fused_encode<S, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+    e = cudaFuncSetAttribute(k_fused_encode<S, T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e == cudaSuccess) {                                                                                   \
       cudaLaunchConfig_t cfg = {};                                                                            \
       cfg.gridDim = dim3(pairs * 2); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st; \
@@ -652,11 +730,12 @@ int launch_fused_encode(const car_render_args &a, int g0, int g1, const float *g
       at[0].id = cudaLaunchAttributeClusterDimension;                                                         \
       at[0].val.clusterDim.x = p.cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                  \
       cfg.attrs = at; cfg.numAttrs = 1;                                                                       \
-      e = cudaLaunchKernelEx(&cfg, k_fused_encode<S, T>, t1h, t1l, tfh, tfl, p);                              \
+      e = cudaLaunchKernelEx(&cfg, k_fused_encode<S, T, K>, t1h, t1l, tfh, tfl, p);                           \
     }                                                                                                         \
   } while (0)
-  if (split3) { if (a.feat_bf16) CAR_LAUNCH(3, __nv_bfloat16); else CAR_LAUNCH(3, float); }
-  else { if (a.feat_bf16) CAR_LAUNCH(1, __nv_bfloat16); else CAR_LAUNCH(1, float); }
+  if (split3) { if (a.feat_bf16) CAR_LAUNCH(3, __nv_bfloat16, 32); else CAR_LAUNCH(3, float, 32); }
+  else if (KS == 64) { if (a.feat_bf16) CAR_LAUNCH(1, __nv_bfloat16, 64); else CAR_LAUNCH(1, float, 64); }
+  else { if (a.feat_bf16) CAR_LAUNCH(1, __nv_bfloat16, 32); else CAR_LAUNCH(1, float, 32); }
 #undef CAR_LAUNCH
   prof_post(st);
   if (e != cudaSuccess) { set_error("fused encode: %s", cudaGetErrorString(e)); return (int)e; }

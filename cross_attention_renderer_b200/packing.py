@@ -78,11 +78,22 @@ class PackedWeights:
         fold = torch.cat([w3[:, :288] @ w2, w3[:, 288:] @ w2], dim=1)            # (416, 1152)
         bfold = w3 @ torch.cat([b2, b2]) + b3
         self.m["kv_fold"] = P(fold.float(), bfold.float())
+        # the same matrix with its K columns in the order of the fused kernel's 64-wide H stages
+        # (include/car_b200.h, car_weights::kv_fold64)
+        perm = torch.empty(1152, dtype=torch.long)
+        for v in range(2):
+            for q in range(9):
+                c, j = divmod(q, 3)
+                for h in range(2):
+                    dst = v * 576 + q * 64 + h * 32
+                    src = v * 576 + c * 192 + h * 96 + j * 32
+                    perm[dst:dst + 32] = torch.arange(src, src + 32)
+        self.m["kv_fold64"] = P(fold.float()[:, perm.to(fold.device)], bfold.float())
 
     def c_struct(self):
         w = _lib.car_weights()
         for name in ("enc1", "enc2", "value", "key1", "key2", "qry1", "qry2", "rep1_loc",
-                     "rep1_g", "rep2", "enc_lat", "phi_in", "phi_out", "kv_fold"):
+                     "rep1_g", "rep2", "enc_lat", "phi_in", "phi_out", "kv_fold", "kv_fold64"):
             setattr(w, name, self.m[name].c_struct())
         for i in range(3):
             w.phi_z[i] = self.m[f"phi_z{i}"].c_struct()
@@ -98,7 +109,7 @@ class PackedGrads:
     def __init__(self, pw):
         self.g = {}
         for name, m in pw.m.items():
-            if name == "kv_fold":
+            if name in ("kv_fold", "kv_fold64"):
                 continue
             w = torch.zeros_like(m.f32)
             b = None if m.bias is None else torch.zeros_like(m.bias)

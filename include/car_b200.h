@@ -90,6 +90,11 @@ typedef struct car_weights {
    * bias = W3 @ [b2;b2] + [b_value; b_key].  Rows 0..287 -> V, rows 288..415 -> key_map pre-ReLU.
    * Used by the fused kernel (tensor-core precisions, P == 64).  N=416 K=1152. */
   car_mat kv_fold;
+  /* kv_fold with its K columns permuted into the order in which the fused kernel's epilogue produces the
+   * hidden activations when it runs 64-wide K stages (bf16 mode): for view v, accumulator block q = 0..8
+   * (c = q / 3, j = q % 3), lane half h, i < 32:  column v*576 + q*64 + h*32 + i  holds kv_fold column
+   * v*576 + c*192 + h*96 + j*32 + i.  Same bias.  hi == NULL: the kernel falls back to 32-wide stages. */
+  car_mat kv_fold64;
 } car_weights;
 
 /* ------------------------------------------------------------------------

@@ -20,11 +20,11 @@ with torch.no_grad():
 s = stats.cpu().tolist()
 names = {0: "mma:a1_empty", 1: "mma:x_full", 2: "mma:b_full(g1)", 3: "mma:a3_empty", 4: "mma:h_full", 5: "mma:b_full(g3)", 6: "mma:TOTAL",
          8: "epi:a1_full", 9: "epi:h_empty", 10: "epi:a3_full", 11: "epi:compute+sts", 12: "epi:fence", 13: "epi:arrive", 14: "epi:a3 drain", 15: "epi:TOTAL",
-         16: "prod:x_empty", 17: "prod:TOTAL", 18: "prod:bar", 19: "prod:fence+arrive", 20: "tma:b_empty", 21: "tma:TOTAL"}
+         16: "prod:x_empty", 17: "prod:TOTAL", 18: "prod:bar", 19: "prod:fence+arrive", 20: "tma:b_empty", 21: "tma:TOTAL", 22: "epi:a3 flush (bar+copy)"}
 rays_pair0 = (b * H * H + 73) // 74
 print(f"precision {prec}: pair-0 rays ~{rays_pair0}")
 for k, n in names.items():
-    tot = s[6] if k < 8 else s[15] if k < 16 else s[17] if k < 20 else s[21]
+    tot = s[6] if k < 8 else s[15] if (k < 16 or k == 22) else s[17] if k < 20 else s[21]
     print(f"  {n:18s} {100.0 * s[k] / max(1, tot):6.1f}%   {s[k] / rays_pair0:10.0f} cyc/ray")
 
 tn = ["drain(hidden)", "wait MMA (scores)", "scores", "softmax + outputs", "post weights (a_empty)", "TOTAL"]

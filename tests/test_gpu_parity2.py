@@ -64,7 +64,9 @@ def test_bf16_psnr_vs_target_within_hundredth_db():
         ref = orc.render(sd, inp, z, H, H, P, interval=interval, cams=cams)
     out = run_cuda(make_model(sd, P, H, precision="bf16"), inp, z, cams=cams, interval=interval)
     g = torch.Generator().manual_seed(5)
-    target = (ref["rgb"] + 0.1 * torch.randn(ref["rgb"].shape, generator=g)).clamp(-1.5, 1.5)
+    # a target ~21 dB away from the render (what 2-view novel-view synthesis scores on real data), unclamped:
+    # with random weights rgb is not confined to [-1, 1]
+    target = ref["rgb"] + 0.18 * torch.randn(ref["rgb"].shape, generator=g)
     p_ref, p_new = orc.psnr(ref["rgb"], target), orc.psnr(cpu(out["rgb"]), target)
     print(f"bf16: psnr vs oracle {orc.psnr(cpu(out['rgb']), ref['rgb']):.2f} dB; vs target {p_new:.4f} / oracle {p_ref:.4f} dB")
     assert 10.0 < p_ref < 40.0
