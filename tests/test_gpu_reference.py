@@ -11,7 +11,17 @@ every map level, derived from ``pixel_val`` with PyTorch's CUDA formula) equal; 
 The reference's own CUDA arithmetic for the geometry stages (cuBLAS bmm for the K=3/K=4 einsums, a
 reciprocal multiply for ``x / scalar``) differs from the fixed-order fp32 evaluation by ulps, so
 ``pixel_val`` is compared to 1e-5 absolute and the taps on every sample whose coordinate is not within
-that distance of a texel boundary."""
+that distance of a texel boundary.
+
+Ill-conditioned rays.  The reference's algorithm is discontinuous in a few places (a triangulated point
+that crosses the other view's focal plane flips its re-projected sample between "inside the image" and
+"zero padding", models.py:317; geometry.py:386), so one-ulp differences upstream can move single rays by
+more than 1e-4.  Measured on the B200 (scripts/diag_ref_gpu.py, 256x256 maps, 64 samples, 1024 rays): the
+unmodified reference run on the GPU and the same code run on the host disagree on 16 rays, up to 5e-4; this
+implementation disagrees with the GPU run on 2 rays, up to 1.5e-4, and agrees with the host run to 7e-5 when
+fed the host's 4x4 matrices.  The reference's own device-to-device disagreement is therefore the noise
+floor: the test requires >= 99.5 % of the rays within 1e-4, and that the worst ray and the number of rays
+above 1e-4 do not exceed what the reference shows against itself (GPU run vs host run) on the same inputs."""
 import pytest
 import torch
 
@@ -79,7 +89,18 @@ def test_forward_matches_unmodified_reference_on_gpu(name):
         print(f"[{name}] level {s}: taps differ on {int(neq.sum())} samples ({int((neq & safe).sum())} away from a texel boundary)")
         assert int((neq & safe).sum()) == 0
         assert float(neq.float().mean()) < 1e-4
-    assert err < 1e-4
+    n_bad = int((per_ray > 1e-4).sum())
+    assert n_bad <= 0.005 * per_ray.numel(), (n_bad, per_ray.numel())
+    if err >= 1e-4:
+        # noise floor: the same reference code on the host vs on the GPU, identical inputs
+        with ref_loader.host_mode():
+            ref_host_model = ref_loader.build_model(sd, H, P, device="cpu")
+            ref_host = ref_loader.render(ref_host_model, synthetic.to_device(inp, "cpu"), [t.cpu() for t in z], chunk_rays=2048)
+        self_ray = (cpu(ref_host["rgb"]) - rrgb).abs().amax(dim=-1).reshape(-1) / rrgb.abs().max()
+        self_bad, self_max = int((self_ray > 1e-4).sum()), float(self_ray.max())
+        print(f"[{name}] reference GPU-vs-host: max {self_max:.3e}, {self_bad} rays above 1e-4; "
+              f"this implementation vs reference-on-GPU: max {err:.3e}, {n_bad} rays")
+        assert err <= self_max and n_bad <= self_bad, (err, self_max, n_bad, self_bad)
     assert torch.allclose(cpu(out["coords"]), cpu(ref["coords"]), rtol=1e-5, atol=1e-6)
     assert torch.allclose(cpu(out["at_wt"]), cpu(ref["at_wt"]), rtol=2e-3, atol=1e-6)
     aw = cpu(ref["at_wt"])
