@@ -59,6 +59,26 @@ class car_render_args(C.Structure):
                 ("train", C.c_int32), ("chunk_rays", C.c_int32)]
 
 
+class car_general_weights(C.Structure):
+    _fields_ = [("enc1", car_mat), ("enc2", car_mat), ("merge", car_mat), ("value", car_mat), ("key1", car_mat),
+                ("key2", car_mat), ("qry1", car_mat), ("qry2", car_mat), ("rep1_loc", car_mat), ("rep1_g", car_mat),
+                ("rep2", car_mat), ("enc_lat", car_mat), ("phi_in", car_mat), ("phi_z", car_mat * 3),
+                ("phi_fc0", car_mat * 3), ("phi_fc1", car_mat * 3), ("phi_out", car_mat)]
+
+
+class car_general_args(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("n_view", C.c_int32), ("flags", C.c_int32),
+                ("b", C.c_int32), ("R", C.c_int32), ("P", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("ray_begin", C.c_int32), ("ray_end", C.c_int32), ("feat", c_fp * 3),
+                ("weights", car_general_weights), ("cams", car_cameras), ("uv", c_fp), ("interval", c_fp),
+                ("rgb", c_fp), ("valid_mask", c_fp), ("depth_ray", c_fp), ("at_wt", c_fp), ("at_wt_max", c_fp),
+                ("pixel_val", c_fp), ("coords", c_fp), ("workspace", c_fp), ("workspace_bytes", C.c_size_t),
+                ("stream", c_fp), ("chunk_rays", C.c_int32), ("debug_interp", c_fp), ("debug_zfinal", c_fp)]
+
+
+FLAG_NO_SAMPLE, FLAG_NO_LATENT_CONCAT = 1, 2
+
+
 class car_mat_grad(C.Structure):
     _fields_ = [("w", c_fp), ("bias", c_fp)]
 
@@ -93,6 +113,9 @@ SYMBOLS = {
     "car_backward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "car_render_backward": (C.c_int, [C.POINTER(car_backward_args)]),
     "car_unpack_features": (C.c_int, [c_fp, c_fp, C.c_int, C.c_int, C.c_int, C.c_int, c_fp]),
+    "car_general_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
+    "car_general_default_chunk_rays": (C.c_int, [C.c_int] * 3),
+    "car_render_forward_general": (C.c_int, [C.POINTER(car_general_args)]),
     "car_last_launch_count": (C.c_int, []),
     "car_profile_begin": (C.c_int, []),
     "car_profile_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]),

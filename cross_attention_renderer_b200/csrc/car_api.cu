@@ -25,6 +25,7 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+void reset_launch_count() { g_launches = 0; }
 int sm_count() {
   static int cache[64] = {0};
   int dev = 0;

@@ -14,7 +14,7 @@ namespace car {
 namespace {
 
 constexpr int ATT_THREADS = 128;
-constexpr int MAX_ROWS = 512;      // 2 * P, P <= 256
+constexpr int MAX_ROWS = 768;      // n * P: 2 * 256 on the n_view = 2 path, 3 * 256 on the general one
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -159,7 +159,147 @@ __global__ void k_finalize(car_render_args a, int g0, int g1, const float *__res
     a.rgb[(size_t)g * 3 + c] = rgb3[(size_t)gl * 3 + c] * valid + 1.f * (1.f - valid);
 }
 
+// ---- general branches: n contexts, latent width L (car_general_args) ------------------------------
+__global__ void __launch_bounds__(ATT_THREADS)
+k_attention1_g(car_general_args a, int n, int L, int g0, const float *__restrict__ key, const float *__restrict__ q1,
+               const float *__restrict__ value, const float *__restrict__ geom, float *__restrict__ zsum) {
+  __shared__ float sc[MAX_ROWS];
+  __shared__ float red[16];
+  int gl = blockIdx.x, g = g0 + gl;
+  int s = g / a.R, r = g - s * a.R;
+  int P = a.P, rows = n * P;
+  size_t row0 = (size_t)gl * rows;
+  scores_softmax(key + row0 * 128, q1 + row0 * 128, rows, sc, red);
+  for (int i = threadIdx.x; i < rows; i += ATT_THREADS) {
+    int j = i / P, k = i - j * P;
+    a.at_wt[((size_t)(s * n + j) * a.R + r) * P + k] = sc[i];
+  }
+  if (threadIdx.x < n) {                                  // per-context argmax, first maximum (models.py:574)
+    int j = threadIdx.x;
+    float best = sc[j * P];
+    int bi = 0;
+    for (int k = 1; k < P; ++k)
+      if (sc[j * P + k] > best) { best = sc[j * P + k]; bi = k; }
+    a.at_wt_max[(size_t)(s * n + j) * a.R + r] = bi;
+  }
+  // z_sum = sum over contexts of the per-context weighted sums, contexts added in order (models.py:537-540)
+  for (int c = threadIdx.x; c < L; c += ATT_THREADS) {
+    const float *v = value + row0 * L + c;
+    float z = 0.f;
+    for (int j = 0; j < n; ++j) {
+      float zj = 0.f;
+      for (int k = 0; k < P; ++k) zj += sc[j * P + k] * v[(size_t)(j * P + k) * L];
+      z = j == 0 ? zj : z + zj;
+    }
+    zsum[(size_t)gl * L + c] = z;
+  }
+  // expected 3-D point: per context, summed over contexts, then the query camera's inverse (models.py:577-590)
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + 3 * n) {
+    int t = threadIdx.x - 32, j = t / 3, comp = t - j * 3;
+    const float *G = geom + (row0 + (size_t)j * P) * CAR_GG_STRIDE + GG_PTC + comp;
+    float w = 0.f;
+    for (int k = 0; k < P; ++k) w += sc[j * P + k] * G[(size_t)k * CAR_GG_STRIDE];
+    red[4 + t] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float x = red[4], y = red[5], z = red[6];
+    for (int j = 1; j < n; ++j) { x += red[4 + 3 * j]; y += red[5 + 3 * j]; z += red[6 + 3 * j]; }
+    const float *qi = a.cams.qinv + (size_t)s * 16;
+    float zc = ((qi[8] * x + qi[9] * y) + qi[10] * z) + qi[11];
+    a.depth_ray[(size_t)s * a.R + r] = fminf(fmaxf(zc, 0.f), 10.f);
+  }
+}
+
+__global__ void __launch_bounds__(ATT_THREADS)
+k_attention2_g(car_general_args a, int n, int L, int g0, const float *__restrict__ q2, const float *__restrict__ q1,
+               const float *__restrict__ value, const float *__restrict__ zsum, float *__restrict__ zfin) {
+  __shared__ float sc[MAX_ROWS];
+  __shared__ float red[16];
+  int gl = blockIdx.x;
+  int P = a.P, rows = n * P;
+  size_t row0 = (size_t)gl * rows;
+  scores_softmax(q2 + row0 * 128, q1 + row0 * 128, rows, sc, red);
+  // per context: sum_k a2 * V + z_sum, then summed over the contexts (models.py:561-564)
+  for (int c = threadIdx.x; c < L; c += ATT_THREADS) {
+    const float *v = value + row0 * L + c;
+    const float zs = zsum[(size_t)gl * L + c];
+    float z = 0.f;
+    for (int j = 0; j < n; ++j) {
+      float zj = 0.f;
+      for (int k = 0; k < P; ++k) zj += sc[j * P + k] * v[(size_t)(j * P + k) * L];
+      z = j == 0 ? (zj + zs) : z + (zj + zs);
+    }
+    zfin[(size_t)gl * L + c] = z;
+  }
+}
+
+// coords (9 per context) padded to 32: [d_0 m_0 o_0 | d_1 m_1 o_1 | ... | 0]  (models.py:597-602)
+__global__ void k_phi_prep_g(car_general_args a, int g0, int g1, float *__restrict__ c32) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (g1 - g0) * 32) return;
+  int gl = idx >> 5, c = idx & 31;
+  int g = g0 + gl, s = g / a.R, r = g - s * a.R;
+  float v = 0.f;
+  if (c < 9 * a.n_view) {
+    int j = c / 9, q = c - j * 9;
+    v = a.coords[((size_t)(s * a.n_view + j) * a.R + r) * 9 + q];
+  }
+  c32[idx] = v;
+}
+
+__global__ void k_finalize_g(car_general_args a, int g0, int g1, const float *__restrict__ rgb3,
+                             const uint8_t *__restrict__ overlap) {
+  int gl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gl >= g1 - g0) return;
+  int g = g0 + gl;
+  int any = 0;
+  for (int j = 0; j < a.n_view; ++j) any |= overlap[gl * a.n_view + j];
+  float valid = any ? 1.f : 0.f;
+  a.valid_mask[g] = valid;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    a.rgb[(size_t)g * 3 + c] = rgb3[(size_t)gl * 3 + c] * valid + 1.f * (1.f - valid);
+}
+
 }  // namespace
+
+void launch_attention1_general(const car_general_args &a, const GenShape &gs, int g0, int g1, const float *key, const float *q1,
+                               const float *value, const float *geom, float *zsum, cudaStream_t st) {
+  if (g1 <= g0) return;
+  prof_pre(CAR_ST_ATTENTION, st);
+  k_attention1_g<<<g1 - g0, ATT_THREADS, 0, st>>>(a, gs.n, gs.L, g0, key, q1, value, geom, zsum);
+  prof_post(st);
+  count_launch();
+}
+
+void launch_attention2_general(const car_general_args &a, const GenShape &gs, int g0, int g1, const float *q2, const float *q1,
+                               const float *value, const float *zsum, float *zfin, cudaStream_t st) {
+  if (g1 <= g0) return;
+  prof_pre(CAR_ST_ATTENTION, st);
+  k_attention2_g<<<g1 - g0, ATT_THREADS, 0, st>>>(a, gs.n, gs.L, g0, q2, q1, value, zsum, zfin);
+  prof_post(st);
+  count_launch();
+}
+
+void launch_phi_prep_general(const car_general_args &a, int g0, int g1, float *c32, cudaStream_t st) {
+  int n = (g1 - g0) * 32;
+  if (n <= 0) return;
+  prof_pre(CAR_ST_PHI, st);
+  k_phi_prep_g<<<(n + 255) / 256, 256, 0, st>>>(a, g0, g1, c32);
+  prof_post(st);
+  count_launch();
+}
+
+void launch_finalize_general(const car_general_args &a, int g0, int g1, const float *rgb3, const uint8_t *overlap,
+                             cudaStream_t st) {
+  int n = g1 - g0;
+  if (n <= 0) return;
+  prof_pre(CAR_ST_PHI, st);
+  k_finalize_g<<<(n + 127) / 128, 128, 0, st>>>(a, g0, g1, rgb3, overlap);
+  prof_post(st);
+  count_launch();
+}
 
 void launch_attention1(const car_render_args &a, int g0, int g1, const float *key, const float *q1,
                        const float *value, const float *geom, float *zsum, float *,

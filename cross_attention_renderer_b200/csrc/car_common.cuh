@@ -26,6 +26,7 @@ namespace car {
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
+void reset_launch_count();
 int sm_count();                     // multiprocessors of the CURRENT device (cached per device)
 // Profiling hooks (car_profile_begin/end): call around a kernel launch.
 void prof_pre(int stage, cudaStream_t st);
@@ -106,6 +107,38 @@ int launch_tail(const car_render_args &a, int phase, int g0, int g1, const float
                 const uint16_t *kh_hi, const uint16_t *kh_lo, float *q1, float *zsum, const float *rowbias,
                 float *zfin, cudaStream_t st);
 
+
+// ---- general branches (n_view 1 / 3, no_sample, no_latent_concat): car_general.cu ----------
+#define CAR_GG_STRIDE 48     // floats per sample row in the general geometry record
+enum {
+  GG_GX = 0, GG_GY = 1,      // primary grid coords
+  GG_C0 = 2, GG_C1 = 4,      // cross-view grid coords of encoder parts 1 and 2 (x, y each)
+  GG_T = 6,                  // tanh triples of parts 0, 1, 2 (n_view = 1: tanh(pt/5), tanh(pt/100))
+  GG_PTC = 15,               // clamp(pt, -100, 100) [3]
+  GG_LOCAL = 32,             // local_coords [16]
+};
+struct GenShape {             // derived sizes of a general-branch call
+  int n, flags, parts, xw, ci, L;   // contexts; flags; encoder parts per row; X width per part; interp width; latent width
+};
+inline GenShape gen_shape(int n_view, int flags) {
+  GenShape g;
+  g.n = n_view; g.flags = flags;
+  const bool noconcat = (flags & CAR_FLAG_NO_LATENT_CONCAT) != 0;
+  g.parts = noconcat ? 1 : (n_view == 1 ? 1 : n_view);
+  g.xw = noconcat ? CAR_C_FEAT : CAR_K_ENC;
+  g.ci = noconcat ? CAR_C_FEAT : (n_view == 1 ? CAR_C_FEAT : CAR_C_LAT * n_view);
+  g.L = (noconcat || n_view == 1) ? CAR_C_FEAT : CAR_C_LAT;
+  return g;
+}
+void launch_ray_setup_general(const car_general_args &a, int g0, int g1, RaySeg *seg, uint8_t *overlap, cudaStream_t st);
+void launch_sample_geometry_general(const car_general_args &a, int g0, int g1, const RaySeg *seg, float *geom, cudaStream_t st);
+void launch_gather_general(const car_general_args &a, const GenShape &gs, int g0, int g1, const float *geom, float *x, cudaStream_t st);
+void launch_attention1_general(const car_general_args &a, const GenShape &gs, int g0, int g1, const float *key, const float *q1,
+                               const float *value, const float *geom, float *zsum, cudaStream_t st);
+void launch_attention2_general(const car_general_args &a, const GenShape &gs, int g0, int g1, const float *q2, const float *q1,
+                               const float *value, const float *zsum, float *zfin, cudaStream_t st);
+void launch_phi_prep_general(const car_general_args &a, int g0, int g1, float *c32, cudaStream_t st);
+void launch_finalize_general(const car_general_args &a, int g0, int g1, const float *rgb3, const uint8_t *overlap, cudaStream_t st);
 
 // ---- car_api.cu: workspace carve-up for one ray chunk ------------------------------------
 struct Workspace {

@@ -191,6 +191,67 @@ k_gather(car_render_args a, int g0, int g1, const float *__restrict__ geom, OUT 
   }
 }
 
+// General branches (car_b200.h, car_general_args): one warp per sample row, fp32 output.
+//   parts == 1, xw == 592 (n_view = 1): [own 576 | tanh(pt/5) 3 | tanh(pt/100) 3 | 0]
+//   parts == 1, xw == 576 (no_latent_concat): [own 576]
+//   parts == 2 (n_view = 2):  slot j = own view (border taps), slot 1-j = the other view at the re-projected point
+//   parts == 3 (n_view = 3):  part 0 = own view; parts 1, 2 = the other views in ascending order at GG_C0 / GG_C1
+// each part followed by its tanh triple and zero padding to 592 (models.py:330-342, 436-446, 483-485).
+__global__ void __launch_bounds__(256)
+k_gather_g(car_general_args a, GenShape gs, int g0, int g1, const float *__restrict__ geom, float *__restrict__ out) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  const int n = gs.n;
+  long nrows = (long)(g1 - g0) * n * a.P;
+  if (warp >= nrows) return;
+  int rj = warp / a.P;
+  int j = rj % n;
+  int g = g0 + rj / n;
+  int s = g / a.R;
+  const float *G = geom + (size_t)warp * CAR_GG_STRIDE;
+  float *row = out + (size_t)warp * gs.parts * gs.xw;
+  for (int part = 0; part < gs.parts; ++part) {
+    // which view is sampled, where, with which padding, and into which slot
+    int view = j, slot = part;
+    float gx = G[GG_GX], gy = G[GG_GY];
+    bool border = true;
+    if (gs.parts == 2) {
+      if (part == 1) { view = 1 - j; gx = G[GG_C0]; gy = G[GG_C0 + 1]; border = false; }
+      slot = view;                                      // channel halves are ordered (view 0, view 1)
+    } else if (gs.parts == 3 && part > 0) {
+      int idx = 0;
+      for (int jj = 0; jj < 3; ++jj) { if (jj == j) continue; if (++idx == part) { view = jj; break; } }
+      gx = G[part == 1 ? GG_C0 : GG_C1]; gy = G[(part == 1 ? GG_C0 : GG_C1) + 1]; border = false;
+    }
+    float *dst = row + (size_t)slot * gs.xw;
+    int chan0 = 0;
+#pragma unroll
+    for (int lvl = 0; lvl < 3; ++lvl) {
+      int C = lvl == 2 ? 64 : 256;
+      int h = lvl == 0 ? a.H / 4 : (lvl == 1 ? a.H / 2 : a.H);
+      int w = lvl == 0 ? a.W / 4 : (lvl == 1 ? a.W / 2 : a.W);
+      const float *img = a.feat[lvl] + (size_t)(s * n + view) * h * w * C;
+      Taps t = make_taps(gx, gy, w, h, border);
+      for (int c = lane * 4; c < C; c += 128)
+        *reinterpret_cast<float4 *>(dst + chan0 + c) = lerp4(img, C, c, t);
+      chan0 += C;
+    }
+    if (gs.xw > CAR_C_FEAT && lane < 4) {
+      // tail columns 576..591: tanh triple(s), zero padding
+      float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n == 1) {
+        if (lane == 0) t4 = make_float4(G[GG_T], G[GG_T + 1], G[GG_T + 2], G[GG_T + 3]);
+        if (lane == 1) t4 = make_float4(G[GG_T + 4], G[GG_T + 5], 0.f, 0.f);
+      } else if (lane == 0) {
+        // n_view = 2: the triple of the VIEW in this slot (GG_T + 3*view); n_view = 3: the triple of this part
+        const float *T = G + GG_T + 3 * (gs.parts == 2 ? slot : part);
+        t4 = make_float4(T[0], T[1], T[2], 0.f);
+      }
+      *reinterpret_cast<float4 *>(dst + CAR_C_FEAT + lane * 4) = t4;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Backward of the two gathers (grid_sample backward w.r.t. the input maps,
 // ATen/native/cuda/GridSampler.cuh grid_sampler_2d_backward: safe_add_2d of
@@ -310,6 +371,17 @@ void launch_unpack_features(const float *nhwc, float *nchw, int bn, int C, int h
   dim3 grid((hw + 31) / 32, (C + 31) / 32, bn), block(32, 8);
   prof_pre(CAR_ST_PACK, st);
   k_unpack_features<<<grid, block, 0, st>>>(nhwc, nchw, C, hw);
+  prof_post(st);
+  count_launch();
+}
+
+void launch_gather_general(const car_general_args &a, const GenShape &gs, int g0, int g1, const float *geom, float *x,
+                           cudaStream_t st) {
+  long nrows = (long)(g1 - g0) * gs.n * a.P;
+  if (nrows <= 0) return;
+  unsigned blocks = (unsigned)((nrows * 32 + 255) / 256);
+  prof_pre(CAR_ST_GATHER, st);
+  k_gather_g<<<blocks, 256, 0, st>>>(a, gs, g0, g1, geom, x);
   prof_post(st);
   count_launch();
 }

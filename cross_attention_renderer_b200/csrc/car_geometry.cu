@@ -97,27 +97,10 @@ __device__ __forceinline__ float to_grid(float c) {
   return isfinite(g) ? g : 0.0f;
 }
 
-__global__ void k_ray_setup(car_render_args a, int g0, int g1, RaySeg *__restrict__ seg,
-                            uint8_t *__restrict__ overlap) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  int n = (g1 - g0) * 2;
-  if (idx >= n) return;
-  int g = g0 + idx / 2, j = idx & 1;
-  int s = g / a.R, r = g - s * a.R;
-  const float *Q = a.cams.Q + (size_t)(s * 2 + j) * 16;
-  const float *Kq = a.cams.Kq + (size_t)s * 16;
-  const float *K = a.cams.K + (size_t)(s * 2 + j) * 16;
-  float u = a.uv[((size_t)s * a.R + r) * 2 + 0];
-  float v = a.uv[((size_t)s * a.R + r) * 2 + 1];
-  V3 d, m;
-  ray_through_pixel(u, v, Kq[0], Kq[5], Kq[2], Kq[6], Q, d, m);
-  V3 o = {Q[3], Q[7], Q[11]};
-  float *co = a.coords + ((size_t)(s * 2 + j) * a.R + r) * 9;
-  co[0] = d.x; co[1] = d.y; co[2] = d.z;
-  co[3] = m.x; co[4] = m.y; co[5] = m.z;
-  co[6] = o.x; co[7] = o.y; co[8] = o.z;
-
-  float Hf = (float)a.H;
+// Clip the ray (origin o, unit direction d, context frame) to the context image: epipolar.py:175-253 with
+// extrinsics = identity and H-normalised intrinsics (models.py:226-258).  seg = segment end points in grid
+// coordinates after the NaN / Inf scrub; ov = overlaps_image.
+__device__ __forceinline__ void epipolar_clip(const float *__restrict__ K, float Hf, V3 o, V3 d, RaySeg &sg, bool &ov) {
   float Kn[6] = {K[0] / Hf, K[1] / Hf, K[2] / Hf, K[4] / Hf, K[5] / Hf, K[6] / Hf};
   Edge e[4];
   e[0] = frame_edge(0, 0.0f, Kn, o, d);
@@ -152,11 +135,36 @@ __global__ void k_ray_setup(car_render_args a, int g0, int g1, RaySeg *__restric
   float minx = v0 ? x0 : fmin.x, miny = v0 ? y0 : fmin.y;
   float maxx = vi ? xi : fmax.x, maxy = vi ? yi : fmax.y;
   bool minv = v0 || fmin.valid, maxv = vi || fmax.valid;
-  RaySeg sg;
   sg.sx = to_grid(minx); sg.sy = to_grid(miny);
   sg.ex = to_grid(maxx); sg.ey = to_grid(maxy);
+  ov = minv && maxv;
+}
+
+__global__ void k_ray_setup(car_render_args a, int g0, int g1, RaySeg *__restrict__ seg,
+                            uint8_t *__restrict__ overlap) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int n = (g1 - g0) * 2;
+  if (idx >= n) return;
+  int g = g0 + idx / 2, j = idx & 1;
+  int s = g / a.R, r = g - s * a.R;
+  const float *Q = a.cams.Q + (size_t)(s * 2 + j) * 16;
+  const float *Kq = a.cams.Kq + (size_t)s * 16;
+  const float *K = a.cams.K + (size_t)(s * 2 + j) * 16;
+  float u = a.uv[((size_t)s * a.R + r) * 2 + 0];
+  float v = a.uv[((size_t)s * a.R + r) * 2 + 1];
+  V3 d, m;
+  ray_through_pixel(u, v, Kq[0], Kq[5], Kq[2], Kq[6], Q, d, m);
+  V3 o = {Q[3], Q[7], Q[11]};
+  float *co = a.coords + ((size_t)(s * 2 + j) * a.R + r) * 9;
+  co[0] = d.x; co[1] = d.y; co[2] = d.z;
+  co[3] = m.x; co[4] = m.y; co[5] = m.z;
+  co[6] = o.x; co[7] = o.y; co[8] = o.z;
+
+  RaySeg sg;
+  bool ov;
+  epipolar_clip(K, (float)a.H, o, d, sg, ov);
   seg[idx] = sg;
-  overlap[idx] = (minv && maxv) ? 1 : 0;
+  overlap[idx] = ov ? 1 : 0;
 }
 
 __device__ __forceinline__ V3 xform_point(const float *__restrict__ T, V3 p) {
@@ -271,7 +279,192 @@ __global__ void k_sample_geometry(car_render_args a, int g0, int g1,
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// General branches (n_view = 1 / 3, no_sample, no_latent_concat): same arithmetic, n contexts.
+// ---------------------------------------------------------------------------------------
+// geometry.project (geometry.py:374-393) + util.normalize_for_grid_sample (utils/util.py:16-19)
+__device__ __forceinline__ void project_to_grid(V3 p, const float *__restrict__ Kj, float Wm1, float Hm1, float &gx, float &gy) {
+  float xp = Kj[0] * p.x / (p.z + 1e-12f) + Kj[2];
+  float yp = Kj[5] * p.y / (p.z + 1e-12f) + Kj[6];
+  xp = isfinite(xp) ? xp : 1e10f;
+  yp = isfinite(yp) ? yp : 1e10f;
+  gx = (xp / Wm1) * 2.0f - 1.0f;
+  gy = (yp / Hm1) * 2.0f - 1.0f;
+}
+
+// One thread per (ray, context): Plücker coordinates, and either the clipped epipolar segment or
+// (CAR_FLAG_NO_SAMPLE, geometry.py:165-187) the projections of the ray's points at the depths in
+// `interval`, written straight to pixel_val, with valid = any sample strictly inside (-1, 1)^2.
+__global__ void k_ray_setup_g(car_general_args a, int g0, int g1, RaySeg *__restrict__ seg,
+                              uint8_t *__restrict__ overlap) {
+  const int n = a.n_view;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (g1 - g0) * n) return;
+  int g = g0 + idx / n, j = idx % n;
+  int s = g / a.R, r = g - s * a.R;
+  const float *Q = a.cams.Q + (size_t)(s * n + j) * 16;
+  const float *Kq = a.cams.Kq + (size_t)s * 16;
+  const float *K = a.cams.K + (size_t)(s * n + j) * 16;
+  float u = a.uv[((size_t)s * a.R + r) * 2 + 0];
+  float v = a.uv[((size_t)s * a.R + r) * 2 + 1];
+  V3 d, m;
+  ray_through_pixel(u, v, Kq[0], Kq[5], Kq[2], Kq[6], Q, d, m);
+  V3 o = {Q[3], Q[7], Q[11]};
+  float *co = a.coords + ((size_t)(s * n + j) * a.R + r) * 9;
+  co[0] = d.x; co[1] = d.y; co[2] = d.z;
+  co[3] = m.x; co[4] = m.y; co[5] = m.z;
+  co[6] = o.x; co[7] = o.y; co[8] = o.z;
+  RaySeg sg = {0.f, 0.f, 0.f, 0.f};
+  bool ov = false;
+  if (a.flags & CAR_FLAG_NO_SAMPLE) {
+    float *pv = a.pixel_val + (((size_t)(s * n + j) * a.R + r) * a.P) * 2;
+    const float Wm1 = (float)(a.W - 1), Hm1 = (float)(a.H - 1);
+    for (int k = 0; k < a.P; ++k) {
+      const float t = a.interval[k];
+      V3 pt = {o.x + t * d.x, o.y + t * d.y, o.z + t * d.z};
+      float gx, gy;
+      project_to_grid(pt, K, Wm1, Hm1, gx, gy);
+      pv[2 * k] = gx; pv[2 * k + 1] = gy;
+      ov = ov || (gx < 1.0f && gx > -1.0f && gy < 1.0f && gy > -1.0f);
+    }
+  } else {
+    epipolar_clip(K, (float)a.H, o, d, sg, ov);
+  }
+  seg[idx] = sg;
+  overlap[idx] = ov ? 1 : 0;
+}
+
+// One thread per (ray, sample index) handling all n contexts (n_view = 3 needs the triangulated points of
+// the other contexts' samples, models.py:354-423).  Writes the 48-float records (car_common.cuh GG_*).
+__global__ void k_sample_geometry_g(car_general_args a, int g0, int g1, const RaySeg *__restrict__ seg,
+                                    float *__restrict__ geom) {
+  const int n = a.n_view;
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)(g1 - g0) * a.P) return;
+  const int k = (int)(idx % a.P);
+  const int gl = (int)(idx / a.P);
+  const int g = g0 + gl;
+  const int s = g / a.R, r = g - s * a.R;
+  const bool nosample = (a.flags & CAR_FLAG_NO_SAMPLE) != 0;
+  const bool concat = !(a.flags & CAR_FLAG_NO_LATENT_CONCAT);
+  V3 pt[3];
+  float gxs[3], gys[3];
+  for (int j = 0; j < n; ++j) {
+    float gx, gy;
+    float *pv = a.pixel_val + (((size_t)(s * n + j) * a.R + r) * a.P + k) * 2;
+    if (nosample) { gx = pv[0]; gy = pv[1]; }
+    else {
+      const RaySeg sg = seg[gl * n + j];
+      const float iv = a.interval[k];
+      gx = sg.sx + (sg.ex - sg.sx) * iv;
+      gy = sg.sy + (sg.ey - sg.sy) * iv;
+      *reinterpret_cast<float2 *>(pv) = make_float2(gx, gy);
+    }
+    gxs[j] = gx; gys[j] = gy;
+    const float *co = a.coords + ((size_t)(s * n + j) * a.R + r) * 9;
+    V3 d = {co[0], co[1], co[2]}, m = {co[3], co[4], co[5]}, o = {co[6], co[7], co[8]};
+    const float *K = a.cams.K + (size_t)(s * n + j) * 16;
+    const float fx = K[0], fy = K[5], cx = K[2], cy = K[6];
+    const float px = (gx + 1.0f) / 2.0f * (float)(a.W - 1);
+    const float py = (gy + 1.0f) / 2.0f * (float)(a.H - 1);
+    V3 l2f, m2f;
+    ray_through_pixel(px, py, fx, fy, cx, cy, a.cams.Cself + (size_t)(s * n + j) * 16, l2f, m2f);
+    D3 l1 = {(double)d.x, (double)d.y, (double)d.z};
+    D3 m1 = {(double)m.x, (double)m.y, (double)m.z};
+    D3 l2 = {(double)l2f.x, (double)l2f.y, (double)l2f.z};
+    D3 m2 = {(double)m2f.x, (double)m2f.y, (double)m2f.z};
+    D3 nn = cross3d(l1, l2);
+    D3 aa = cross3d(l2, nn);
+    D3 t1 = cross3d(m1, aa);
+    double sdot = (m2.x * nn.x + m2.y * nn.y) + m2.z * nn.z;
+    double nrm = sqrt((nn.x * nn.x + nn.y * nn.y) + nn.z * nn.z);
+    double cd = nrm * nrm + 1e-12;
+    double p1x = (-t1.x + sdot * l1.x) / cd;
+    double p1y = (-t1.y + sdot * l1.y) / cd;
+    double p1z = (-t1.z + sdot * l1.z) / cd;
+    pt[j].x = isfinite(p1x) ? (float)p1x : 0.0f;
+    pt[j].y = isfinite(p1y) ? (float)p1y : 0.0f;
+    pt[j].z = isfinite(p1z) ? (float)p1z : 0.0f;
+    float *G = geom + ((size_t)(gl * n + j) * a.P + k) * CAR_GG_STRIDE;
+    G[GG_GX] = gx; G[GG_GY] = gy;
+    // local_coords = [cam_rays, 0,0,0, ray_dir, tanh(depth/{1,10,100,1000}), ray origin]  (models.py:494-528)
+    const float rx = (px - cx) / fx, ry = (py - cy) / fy;
+    const float rn = fmaxf(norm3(rx, ry, 1.0f), 1e-12f);
+    float *L = G + GG_LOCAL;
+    L[0] = rx / rn; L[1] = ry / rn; L[2] = 1.0f / rn;
+    L[3] = 0.f; L[4] = 0.f; L[5] = 0.f;
+    L[6] = d.x; L[7] = d.y; L[8] = d.z;
+    float depth = norm3(pt[j].x - o.x, pt[j].y - o.y, pt[j].z - o.z);
+    if (!isfinite(depth)) depth = 1000000.0f;
+    L[9] = tanhf(depth);
+    L[10] = tanhf(depth / 10.0f);
+    L[11] = tanhf(depth / 100.0f);
+    L[12] = tanhf(depth / 1000.0f);
+    L[13] = o.x; L[14] = o.y; L[15] = o.z;
+    G[GG_PTC + 0] = fminf(fmaxf(pt[j].x, -100.0f), 100.0f);
+    G[GG_PTC + 1] = fminf(fmaxf(pt[j].y, -100.0f), 100.0f);
+    G[GG_PTC + 2] = fminf(fmaxf(pt[j].z, -100.0f), 100.0f);
+    for (int q = 2; q < GG_PTC; ++q) G[q] = 0.f;
+    for (int q = GG_PTC + 3; q < GG_LOCAL; ++q) G[q] = 0.f;
+  }
+  const float Wm1 = (float)(a.W - 1), Hm1 = (float)(a.H - 1);
+  for (int j = 0; j < n; ++j) {
+    float *G = geom + ((size_t)(gl * n + j) * a.P + k) * CAR_GG_STRIDE;
+    if (n == 1) {
+      // models.py:483: [tanh(pt/5), tanh(pt/100)] (pt already scrubbed, geometry.py:126-127)
+      G[GG_T + 0] = tanhf(pt[0].x / 5.0f); G[GG_T + 1] = tanhf(pt[0].y / 5.0f); G[GG_T + 2] = tanhf(pt[0].z / 5.0f);
+      G[GG_T + 3] = tanhf(pt[0].x / 100.0f); G[GG_T + 4] = tanhf(pt[0].y / 100.0f); G[GG_T + 5] = tanhf(pt[0].z / 100.0f);
+    } else if (!concat) {
+      // raw features only
+    } else if (n == 2) {
+      // models.py:285-342: parts in (view 0, view 1) order; the other view's features at the re-projected point
+      const float *Rel = a.cams.Rel + (size_t)s * 64;               // [k][j][4][4]
+      V3 pv0 = xform_point(Rel + (0 * 2 + j) * 16, pt[j]);
+      V3 pv1 = xform_point(Rel + (1 * 2 + j) * 16, pt[j]);
+      V3 oth = j == 0 ? pv1 : pv0;
+      project_to_grid(oth, a.cams.K + (size_t)(s * 2 + (1 - j)) * 16, Wm1, Hm1, G[GG_C0], G[GG_C0 + 1]);
+      G[GG_T + 0] = tanhf(nan_to_num0(pv0.x) / 5.0f); G[GG_T + 1] = tanhf(nan_to_num0(pv0.y) / 5.0f); G[GG_T + 2] = tanhf(nan_to_num0(pv0.z) / 5.0f);
+      G[GG_T + 3] = tanhf(nan_to_num0(pv1.x) / 5.0f); G[GG_T + 4] = tanhf(nan_to_num0(pv1.y) / 5.0f); G[GG_T + 5] = tanhf(nan_to_num0(pv1.z) / 5.0f);
+    } else {
+      // n_view = 3 (models.py:345-475): row of context a = j.  part 0: own features, tanh(ptv[a][a] / 5); parts 1, 2:
+      // the other contexts jj in ascending order: view jj's maps at project(ptv[a][jj], K_jj) where
+      // ptv[a][jj] = Rel[a][jj] . pt[jj] (the same (ray, sample) of context jj's OWN line), and tanh(ptv[a][jj] / 5)
+      const float *Rel = a.cams.Rel + (size_t)s * 9 * 16 + (size_t)j * 3 * 16;   // Rel[s][a = j][.]
+      V3 own = xform_point(Rel + j * 16, pt[j]);
+      G[GG_T + 0] = tanhf(nan_to_num0(own.x) / 5.0f); G[GG_T + 1] = tanhf(nan_to_num0(own.y) / 5.0f); G[GG_T + 2] = tanhf(nan_to_num0(own.z) / 5.0f);
+      int part = 1;
+      for (int jj = 0; jj < 3; ++jj) {
+        if (jj == j) continue;
+        V3 q = xform_point(Rel + jj * 16, pt[jj]);
+        float *cc = G + (part == 1 ? GG_C0 : GG_C1);
+        project_to_grid(q, a.cams.K + (size_t)(s * 3 + jj) * 16, Wm1, Hm1, cc[0], cc[1]);
+        float *T = G + GG_T + 3 * part;
+        T[0] = tanhf(nan_to_num0(q.x) / 5.0f); T[1] = tanhf(nan_to_num0(q.y) / 5.0f); T[2] = tanhf(nan_to_num0(q.z) / 5.0f);
+        ++part;
+      }
+    }
+  }
+}
+
 }  // namespace
+
+void launch_ray_setup_general(const car_general_args &a, int g0, int g1, RaySeg *seg, uint8_t *overlap, cudaStream_t st) {
+  int n = (g1 - g0) * a.n_view;
+  if (n <= 0) return;
+  prof_pre(CAR_ST_RAYSETUP, st);
+  k_ray_setup_g<<<(n + 127) / 128, 128, 0, st>>>(a, g0, g1, seg, overlap);
+  prof_post(st);
+  count_launch();
+}
+
+void launch_sample_geometry_general(const car_general_args &a, int g0, int g1, const RaySeg *seg, float *geom, cudaStream_t st) {
+  long n = (long)(g1 - g0) * a.P;
+  if (n <= 0) return;
+  prof_pre(CAR_ST_SAMPLE_GEOM, st);
+  k_sample_geometry_g<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(a, g0, g1, seg, geom);
+  prof_post(st);
+  count_launch();
+}
 
 void launch_ray_setup(const car_render_args &a, int g0, int g1, RaySeg *seg, uint8_t *overlap,
                       cudaStream_t st) {

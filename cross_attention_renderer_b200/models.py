@@ -65,24 +65,39 @@ class CrossAttentionRenderer(nn.Module):
         self.num_hidden_units_phi = num_hidden_units_phi
         if model != "midas_vit":
             raise NotImplementedError("only model='midas_vit' (576-channel features) is on the hot path")
-        if n_view != 2 or no_sample or no_latent_concat or not repeat_attention:
-            raise NotImplementedError(
-                "the B200 path covers n_view=2 with default flags (SURVEY.md §8); "
-                "n_view=1/3, no_sample, no_latent_concat are 'next' rows")
+        if n_view not in (1, 2, 3):
+            raise NotImplementedError("the reference defines n_view in {1, 2, 3} (models.py:281,345,478)")
+        if (no_sample or no_latent_concat) and n_view != 2:
+            raise NotImplementedError("no_sample / no_latent_concat are built for n_view=2 (the configurations the "
+                                      "reference's ablation scripts run)")
+        if no_sample and no_latent_concat:
+            raise NotImplementedError("no_sample and no_latent_concat together")
+        if not repeat_attention:
+            raise NotImplementedError("repeat_attention=False (the reference never sets it)")
         if num_hidden_units_phi != 128:
             raise NotImplementedError("num_hidden_units_phi must be 128")
+        # n_view = 2 with the default flags is the fused tcgen05 hot path; every other branch runs the general
+        # exact-fp32 kernels behind car_render_forward_general
+        self.general = n_view != 2 or no_sample or no_latent_concat
         # image encoder: outside the hot path; plug in any module with the reference's
         # encoder.forward(rgb, cam2world_encode, n_view) -> [path_2, path_1] contract
         self.encoder = encoder
         hidden = 128
         latent = 512 + 64
         self.conv_map = nn.Conv2d(3, 64, kernel_size=7, stride=1, padding=3)
-        self.query_encode_latent = nn.Conv2d(latent + 3, latent, 1)
-        self.query_encode_latent_2 = nn.Conv2d(latent, latent // 2, 1)
-        self.latent_dim = latent // 2
-        self.update_val_merge = nn.Conv2d(self.latent_dim * 2 + 6, self.latent_dim, 1)
-        self.latent_value = nn.Conv2d(self.latent_dim * n_view, self.latent_dim, 1)
-        self.key_map = nn.Conv2d(self.latent_dim * n_view, hidden, 1)
+        self.latent_dim = latent
+        if n_view > 1 and not no_latent_concat:                        # models.py:100-105
+            self.query_encode_latent = nn.Conv2d(latent + 3, latent, 1)
+            self.query_encode_latent_2 = nn.Conv2d(latent, latent // 2, 1)
+            self.latent_dim = latent // 2
+            self.update_val_merge = nn.Conv2d(self.latent_dim * 2 + 6, self.latent_dim, 1)
+        elif no_latent_concat:                                         # :106-107
+            self.feature_map = nn.Conv2d(latent, latent // 2, 1)
+        else:                                                          # :108
+            self.update_val_merge = nn.Conv2d(latent + 6, latent, 1)
+        kv_in = self.latent_dim if no_latent_concat else self.latent_dim * n_view      # :116-124
+        self.latent_value = nn.Conv2d(kv_in, self.latent_dim, 1)
+        self.key_map = nn.Conv2d(kv_in, hidden, 1)
         self.key_map_2 = nn.Conv2d(hidden, hidden, 1)
         self.query_embed = nn.Conv2d(16, hidden, 1)
         self.query_embed_2 = nn.Conv2d(hidden, hidden, 1)
@@ -173,8 +188,8 @@ class CrossAttentionRenderer(nn.Module):
         query, context = input["query"], input["context"]
         b, n_context = context["rgb"].shape[:2]
         n_qry, R = query["uv"].shape[1:3]
-        if n_context != 2 or n_qry != 1:
-            raise NotImplementedError("hot path: 2 context views, 1 query view")
+        if n_context != self.n_view or n_qry != 1:
+            raise NotImplementedError(f"{self.n_view} context views (n_view) and 1 query view expected, got {n_context} / {n_qry}")
         if z is None:
             z = z_orig = self.get_z(input)
         else:
@@ -199,14 +214,17 @@ class CrossAttentionRenderer(nn.Module):
         cams = {
             "Q": torch.matmul(Cinv, q).contiguous(),
             "Cself": torch.matmul(Cinv, Cm).contiguous(),
-            "Rel": torch.stack([torch.matmul(inv(Cm[:, k:k + 1]), Cm) for k in range(2)],
-                               dim=1).contiguous(),                     # models.py:285-286
+            "Rel": torch.stack([torch.matmul(inv(Cm[:, k:k + 1]), Cm) for k in range(n_context)],
+                               dim=1).contiguous(),                     # models.py:285-286, 349-352
             "qinv": inv(q[:, 0]).contiguous(),                          # geometry.py:404
             "K": f32(context["intrinsics"]).contiguous(),
             "Kq": f32(query["intrinsics"])[:, 0].contiguous(),
         }
         uv = f32(query["uv"])[:, 0].contiguous()
-        interval = torch.linspace(0, 1, P, device=dev)                  # models.py:261
+        if self.no_sample:
+            interval = torch.linspace(0.1, 10., P, device=dev)          # depths of the volumetric line, geometry.py:175
+        else:
+            interval = torch.linspace(0, 1, P, device=dev)              # models.py:261
         out = self.render_prepared(cams, uv, interval, z, b, R, ray_range=ray_range,
                                    debug_taps=debug_taps)
         out["uv"] = query["uv"]
@@ -225,6 +243,12 @@ class CrossAttentionRenderer(nn.Module):
         # train mode on 192 rays per scene).  It is therefore gated on ``self.training``: a module in
         # eval() mode always runs the configured inference precision, grad mode or not, and its outputs
         # carry no grad_fn (like calling the reference under torch.no_grad(), eval_realestate10k.py:38).
+        if self.general:
+            out = self._launch_general(cams, uv, interval, z, b, R, ray_range, debug_taps)
+            out["at_wts"] = [out["at_wt"]]
+            if self.pixel_val_to_cpu:
+                out["pixel_val"] = out["pixel_val"].cpu()
+            return out
         needs_grad = self.training and torch.is_grad_enabled() and debug_taps is None and (
             any(t.requires_grad for t in z)
             or any(p.requires_grad for n, p in self.named_parameters() if n in HOT_PATH_PARAMS))
@@ -327,6 +351,67 @@ class CrossAttentionRenderer(nn.Module):
         self.last_launch_count = lib.car_last_launch_count()
         keep = (pw, feats, ws, cams, uv, interval)
         return out, a, keep
+
+
+def _launch_general(self, cams, uv, interval, z, b, R, ray_range=None, debug_taps=None):
+    """Fill ``car_general_args`` and enqueue ``car_render_forward_general`` (n_view 1 / 3, no_sample,
+    no_latent_concat; inference only: these branches have no backward kernels)."""
+    lib = _lib.load()
+    dev = z[0].device
+    H, W, P, n = self.H, self.W, self.npoints, self.n_view
+    flags = (_lib.FLAG_NO_SAMPLE if self.no_sample else 0) | (_lib.FLAG_NO_LATENT_CONCAT if self.no_latent_concat else 0)
+    params = {k: v for k, v in self.named_parameters() if not k.startswith("encoder.")}
+    key = tuple((k, v.data_ptr(), v._version) for k, v in params.items())
+    if self._wcache is None or self._wcache[0] != key:
+        self._wcache = (key, packing.PackedGeneralWeights({k: v.detach() for k, v in params.items()}, n,
+                                                          no_latent_concat=self.no_latent_concat))
+    pw = self._wcache[1]
+    feats = self._packed_features(z, False)
+    total = b * R
+    g0, g1 = (0, total) if ray_range is None else ray_range
+    chunk = self.chunk_rays or lib.car_general_default_chunk_rays(n, flags, P)
+    chunk = max(1, min(chunk, g1 - g0))
+    ws = self._workspace(lib.car_general_workspace_bytes(n, flags, P, chunk), dev)
+    out = {
+        "rgb": torch.zeros(b, 1, R, 3, device=dev),
+        "valid_mask": torch.zeros(b, R, 1, device=dev),
+        "depth_ray": torch.zeros(b, R, 1, device=dev),
+        "at_wt": torch.zeros(b * n, R, P, device=dev),
+        "at_wt_max": torch.zeros(b * n, R, 1, dtype=torch.int64, device=dev),
+        "pixel_val": torch.zeros(b * n, R, P, 2, device=dev),
+        "coords": torch.zeros(b * n, R, 9, device=dev),
+    }
+    a = _lib.car_general_args()
+    a.abi_version = _lib.ABI_VERSION
+    a.n_view, a.flags = n, flags
+    a.b, a.R, a.P, a.H, a.W = b, R, P, H, W
+    a.ray_begin, a.ray_end = g0, g1
+    for i in range(3):
+        a.feat[i] = feats[i].data_ptr()
+    a.weights = pw.c_struct()
+    want = {"Q": (b, n, 4, 4), "Cself": (b, n, 4, 4), "Rel": (b, n, n, 4, 4), "qinv": (b, 4, 4), "K": (b, n, 4, 4), "Kq": (b, 4, 4)}
+    for k, shp in want.items():
+        assert cams[k].is_contiguous() and cams[k].dtype == torch.float32 and cams[k].device == dev and tuple(cams[k].shape) == shp, k
+        setattr(a.cams, k, cams[k].data_ptr())
+    a.uv, a.interval = uv.data_ptr(), interval.data_ptr()
+    for k, t in out.items():
+        setattr(a, k, t.data_ptr())
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    a.stream = torch.cuda.current_stream(dev).cuda_stream
+    a.chunk_rays = chunk
+    if debug_taps is not None:
+        rows = (g1 - g0) * n * P
+        ci = 576 if (self.no_latent_concat or n == 1) else 288 * n
+        debug_taps["interp"] = torch.zeros(rows, ci, device=dev)
+        debug_taps["zfinal"] = torch.zeros(g1 - g0, self.latent_dim, device=dev)
+        a.debug_interp, a.debug_zfinal = debug_taps["interp"].data_ptr(), debug_taps["zfinal"].data_ptr()
+    with torch.cuda.device(dev):
+        _lib.check(lib.car_render_forward_general(a), "car_render_forward_general")
+    self.last_launch_count = lib.car_last_launch_count()
+    return out
+
+
+CrossAttentionRenderer._launch_general = _launch_general
 
 
 class _RenderFunction(torch.autograd.Function):

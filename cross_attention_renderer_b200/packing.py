@@ -102,6 +102,61 @@ class PackedWeights:
         return w
 
 
+class PackedGeneralWeights:
+    """``car_general_weights`` (include/car_b200.h) for the other forward branches: n_view in {1, 3} and the
+    no_latent_concat ablation (no_sample uses the n_view = 2 weights unchanged).  Re-groupings on top of
+    ``PackedWeights``': for n_view = 3 the columns of ``latent_value`` / ``key_map`` are re-ordered from the
+    reference's channel-interleaved order (index 3c + k, models.py:444-446) to part-major (k*288 + c), the
+    order in which the kernels write the three encoded parts of a row; ``phi.lin_z`` is summed over its
+    n_view identical column blocks (models.py:604-606); ``phi.lin_in`` is padded from 9*n_view to 32."""
+
+    def __init__(self, sd, n_view, no_latent_concat=False):
+        g = lambda n: sd[n]
+        P = PackedMat
+        self.m = {}
+        concat = n_view > 1 and not no_latent_concat
+        L = 288 if concat else 576
+        if concat:
+            self.m["enc1"] = P(g("query_encode_latent.weight"), g("query_encode_latent.bias"), _lib.K_ENC)
+            self.m["enc2"] = P(g("query_encode_latent_2.weight"), g("query_encode_latent_2.bias"))
+        elif n_view == 1:
+            self.m["merge"] = P(g("update_val_merge.weight"), g("update_val_merge.bias"), _lib.K_ENC)
+        wv = g("latent_value.weight").reshape(L, -1)
+        wk = g("key_map.weight").reshape(128, -1)
+        if concat and n_view == 3:
+            perm = torch.tensor([3 * c + k for k in range(3) for c in range(288)], device=wv.device)
+            wv, wk = wv[:, perm], wk[:, perm]
+        self.m["value"] = P(wv, g("latent_value.bias"))
+        self.m["key1"] = P(wk, g("key_map.bias"))
+        self.m["key2"] = P(g("key_map_2.weight"), g("key_map_2.bias"))
+        self.m["qry1"] = P(g("query_embed.weight"), g("query_embed.bias"))
+        self.m["qry2"] = P(g("query_embed_2.weight"), g("query_embed_2.bias"))
+        rep = g("query_repeat_embed.weight").reshape(128, 144)
+        self.m["rep1_g"] = P(rep[:, :128], g("query_repeat_embed.bias"))
+        self.m["rep1_loc"] = P(rep[:, 128:], None)
+        self.m["rep2"] = P(g("query_repeat_embed_2.weight"), g("query_repeat_embed_2.bias"))
+        self.m["enc_lat"] = P(g("encode_latent.weight"), g("encode_latent.bias"))
+        self.m["phi_in"] = P(g("phi.lin_in.weight"), g("phi.lin_in.bias"), 32)
+        for i in range(3):
+            wz = g(f"phi.lin_z.{i}.weight")
+            self.m[f"phi_z{i}"] = P(sum(wz[:, q * L:(q + 1) * L] for q in range(n_view)), g(f"phi.lin_z.{i}.bias"))
+            self.m[f"phi_fc0{i}"] = P(g(f"phi.blocks.{i}.fc_0.weight"), g(f"phi.blocks.{i}.fc_0.bias"))
+            self.m[f"phi_fc1{i}"] = P(g(f"phi.blocks.{i}.fc_1.weight"), g(f"phi.blocks.{i}.fc_1.bias"))
+        self.m["phi_out"] = P(g("phi.lin_out.weight"), g("phi.lin_out.bias"))
+
+    def c_struct(self):
+        w = _lib.car_general_weights()
+        for name in ("enc1", "enc2", "merge", "value", "key1", "key2", "qry1", "qry2", "rep1_loc", "rep1_g", "rep2",
+                     "enc_lat", "phi_in", "phi_out"):
+            if name in self.m:
+                setattr(w, name, self.m[name].c_struct())
+        for i in range(3):
+            w.phi_z[i] = self.m[f"phi_z{i}"].c_struct()
+            w.phi_fc0[i] = self.m[f"phi_fc0{i}"].c_struct()
+            w.phi_fc1[i] = self.m[f"phi_fc1{i}"].c_struct()
+        return w
+
+
 class PackedGrads:
     """Zero-initialised gradient buffers in the packed layout of ``car_weights``
     (``car_weight_grads``), and the map back to ``state_dict`` shapes."""

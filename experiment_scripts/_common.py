@@ -75,8 +75,6 @@ def base_parser(description, train=False):
 
 
 def build_model(opt, device):
-    if opt.views != 2 or opt.no_sample or opt.no_latent_concat:
-        raise NotImplementedError("the B200 path covers --views 2 with the default sampling flags (SURVEY.md §8)")
     if opt.encoder_module:
         mod, fn = opt.encoder_module.split(":")
         encoder = getattr(importlib.import_module(mod), fn)()

@@ -211,6 +211,61 @@ int car_render_backward(const car_backward_args *args);
 /* NHWC fp32 gradient buffer -> the NCHW layout of the encoder output (inverse of car_pack_features). */
 int car_unpack_features(const float *nhwc, float *nchw, int bn, int C, int h, int w, void *stream);
 
+/* ------------------------------------------------------------------------
+ * The other forward branches of the reference (models.py:219-222, 345-485):
+ *   n_view = 1   one context view, features + [tanh(pt/5), tanh(pt/100)] through update_val_merge (:478-485)
+ *   n_view = 3   three context views, two cross-view gathers per sample, 864-wide interleaved encode (:345-475)
+ *   n_view = 2 with CAR_FLAG_NO_SAMPLE          volumetric line instead of the clipped epipolar segment
+ *                                               (geometry.py:165-187)
+ *   n_view = 2 with CAR_FLAG_NO_LATENT_CONCAT   raw 576-channel features, no per-sample encoder (:476-477)
+ * Same stages as car_render_forward with a different gather fan-out; they run the exact-fp32 kernels
+ * (car_mat::f32 only).  Rows are ((scene*R + ray)*n_view + ctx)*P + sample; outputs have b*n_view leading
+ * dimensions where the n_view = 2 path has b*2.
+ * ---------------------------------------------------------------------- */
+enum { CAR_FLAG_NO_SAMPLE = 1, CAR_FLAG_NO_LATENT_CONCAT = 2 };
+
+typedef struct car_general_weights {
+  car_mat enc1, enc2;   /* query_encode_latent(_2): N=576 K=592 / N=288 K=576 (n_view >= 2 with the latent concat) */
+  car_mat merge;        /* update_val_merge, n_view = 1: N=576 K=592 (582 padded)                                  */
+  car_mat value, key1;  /* latent_value / key_map: K = 576 (n_view 1, no concat) | 576 (n_view 2) | 864 (n_view 3,
+                           columns re-ordered part-major: column k*288 + c holds the reference's column 3c + k)    */
+  car_mat key2, qry1, qry2, rep1_loc, rep1_g, rep2;
+  car_mat enc_lat;      /* N=128 K=L (L = 288, or 576 for n_view = 1 / no concat)                                  */
+  car_mat phi_in;       /* N=128 K=32 (9*n_view padded)                                                           */
+  car_mat phi_z[3];     /* lin_z summed over its n_view column blocks: N=128 K=L                                  */
+  car_mat phi_fc0[3], phi_fc1[3];
+  car_mat phi_out;
+} car_general_weights;
+
+typedef struct car_general_args {
+  int32_t abi_version;
+  int32_t n_view, flags;
+  int32_t b, R, P, H, W;
+  int32_t ray_begin, ray_end;
+  const float *feat[3];           /* packed NHWC fp32 levels, (b*n_view, h_l, w_l, C_l)               */
+  car_general_weights weights;
+  car_cameras cams;               /* Q, Cself, K: (b,n,4,4); Rel: (b,n,n,4,4); qinv, Kq: (b,4,4)       */
+  const float *uv;                /* (b,R,2)                                                          */
+  const float *interval;          /* (P): linspace(0,1,P), or the depths linspace(0.1,10,P) with CAR_FLAG_NO_SAMPLE */
+  float *rgb;                     /* (b,1,R,3)   */
+  float *valid_mask;              /* (b,R,1)     */
+  float *depth_ray;               /* (b,R,1)     */
+  float *at_wt;                   /* (b*n,R,P)   */
+  int64_t *at_wt_max;             /* (b*n,R,1)   */
+  float *pixel_val;               /* (b*n,R,P,2) */
+  float *coords;                  /* (b*n,R,9)   */
+  void *workspace;                /* >= car_general_workspace_bytes(n_view, flags, P, chunk)          */
+  size_t workspace_bytes;
+  void *stream;
+  int32_t chunk_rays;             /* 0 = car_general_default_chunk_rays                               */
+  float *debug_interp;            /* optional (rows, Ci) dump of the per-sample features fed to latent_value / key_map */
+  float *debug_zfinal;            /* optional (rays, L)                                               */
+} car_general_args;
+
+size_t car_general_workspace_bytes(int n_view, int flags, int P, int chunk_rays);
+int car_general_default_chunk_rays(int n_view, int flags, int P);
+int car_render_forward_general(const car_general_args *args);
+
 /* Number of kernels the last car_render_forward / car_render_backward on this thread launched. */
 int car_last_launch_count(void);
 

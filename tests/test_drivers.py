@@ -28,11 +28,14 @@ def test_reference_flag_surface():
     assert C.base_parser("t").parse_args(["--experiment_name", "e"]).batch_size == 48
 
 
-def test_unsupported_branches_fail_loudly():
+def test_branch_flags_reach_the_model():
     opt = C.base_parser("t").parse_args(["--experiment_name", "e", "--views", "3"])
-    with pytest.raises(NotImplementedError):
-        C.build_model(opt, "cpu")
+    m = C.build_model(opt, "cpu")
+    assert m.n_view == 3 and m.general
     opt = C.base_parser("t").parse_args(["--experiment_name", "e", "--no_sample"])
+    m = C.build_model(opt, "cpu")
+    assert m.no_sample and m.general
+    opt = C.base_parser("t").parse_args(["--experiment_name", "e", "--views", "4"])
     with pytest.raises(NotImplementedError):
         C.build_model(opt, "cpu")
 
@@ -53,7 +56,10 @@ def test_checkpoint_format_roundtrip(tmp_path):
     # a reference checkpoint carries encoder.* keys of the DPT encoder: extra / missing keys must not raise
     ck["model"]["encoder.pretrained.model.cls_token"] = torch.zeros(1)
     torch.save(ck, path)
-    missing, unexpected = C.load_checkpoint(m2, path)
+    # ... but silently running the trained renderer on a different encoder is refused unless asked for
+    with pytest.raises(RuntimeError, match="encoder"):
+        C.load_checkpoint(m2, path)
+    missing, unexpected = C.load_checkpoint(m2, path, allow_encoder_mismatch=True)
     assert "encoder.pretrained.model.cls_token" in unexpected
     assert torch.equal(m2.phi.lin_out.weight, m.phi.lin_out.weight)
 

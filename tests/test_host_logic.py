@@ -32,14 +32,24 @@ def test_constructor_signature_matches_reference():
     assert list(fsig.parameters)[1:5] == ["input", "z", "val", "debug"]
 
 
-def test_load_synthetic_state_dict_and_unsupported_branches():
+def test_load_synthetic_state_dict_and_constructor_branches():
     m = CrossAttentionRenderer(n_view=2, npoints=32)
     missing, unexpected = m.load_state_dict(synthetic.make_state_dict(0), strict=False)
     assert not missing and not unexpected
+    # every branch of the reference's constructor creates exactly the reference's parameter set
+    # (params.py is checked against the unmodified reference in tests/golden/make_golden_nview.py)
+    from cross_attention_renderer_b200.params import renderer_param_shapes
+    for kw in (dict(n_view=1), dict(n_view=3), dict(n_view=2, no_sample=True), dict(n_view=2, no_latent_concat=True)):
+        mm = CrossAttentionRenderer(npoints=16, **kw)
+        want = renderer_param_shapes(kw["n_view"], no_latent_concat=kw.get("no_latent_concat", False))
+        got = {k: tuple(v.shape) for k, v in mm.state_dict().items() if not k.startswith("encoder.")}
+        assert got == {k: tuple(v) for k, v in want.items()}, kw
+        assert mm.general
+    assert not m.general
     with pytest.raises(NotImplementedError):
-        CrossAttentionRenderer(n_view=3)
+        CrossAttentionRenderer(n_view=4)
     with pytest.raises(NotImplementedError):
-        CrossAttentionRenderer(n_view=2, no_sample=True)
+        CrossAttentionRenderer(n_view=3, no_sample=True)
 
 
 def test_packing_algebra():
