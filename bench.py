@@ -425,6 +425,57 @@ def measure(ctx, precision, b, H, P, steps, warmup, e2e_steps, with_clocks, seed
     return res
 
 
+def strong_scaling(ctx, scenes_total, H, P, reps):
+    """`scenes_total` scenes, ONE at a time: features on rank 0 only, NCCL broadcast (one scene ahead, overlapped
+    with the previous scene's rendering), each rank renders 1/N of the scene's rays, tiles all-gathered.  Device
+    time, max over ranks; the same with the broadcast disabled (every rank already holds the maps) isolates its cost."""
+    import torch.distributed as dist
+    from cross_attention_renderer_b200 import sharding
+    from cross_attention_renderer_b200.models import CrossAttentionRenderer
+    world, rank, dev = ctx["world"], ctx["rank"], ctx["dev"]
+    model = CrossAttentionRenderer(n_view=2, npoints=P, precision="fp32").to(dev).eval()
+    model.load_state_dict(synthetic.make_state_dict(seed=0), strict=False)
+    model.H = model.W = H
+    model.pixel_val_to_cpu = False
+    scenes, local = [], []
+    for k in range(scenes_total):
+        inp = synthetic.to_device(synthetic.make_inputs(1, H, H, seed=500 + k), dev)
+        z = [t.to(dev) for t in synthetic.make_features(1, H, seed=500 + k)]
+        scenes.append((inp, z if rank == 0 else None))
+        local.append((inp, z))
+
+    def timed(fn):
+        fn()
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    nb = [0]
+
+    def with_bcast():
+        with torch.no_grad():
+            _, nb[0] = sharding.render_scenes_pipelined(model, scenes, src=0, device=dev)
+
+    def without_bcast():
+        with torch.no_grad():
+            for inp, z in local:
+                sharding.render_sharded(model, inp, z, rank=rank, world=world, gather=True)
+    ms_b, ms_n = timed(with_bcast), timed(without_bcast)
+    rays = scenes_total * H * H
+    return {"workload": f"{scenes_total} scenes of {H}x{H} rays, {P} samples, rendered one scene at a time with the rays of "
+                        f"each scene split across {world} GPUs; fp32 maps broadcast from rank 0 (NCCL), one scene ahead",
+            "value": rays / (ms_b * 1e-3), "unit": "rays/s", "ms": ms_b, "scaling": "strong",
+            "ms_maps_already_resident": ms_n, "value_maps_already_resident": rays / (ms_n * 1e-3),
+            "broadcast_bytes_per_rank": nb[0], "broadcast_exposed_ms": ms_b - ms_n,
+            "broadcast_gbs_if_serial": nb[0] / max(1e-9, (ms_b - ms_n) * 1e-3) / 1e9 if ms_b > ms_n else None}
+
+
 def reference_on_gpu(dev, H, P, rays=8192):
     """the unmodified reference (oracle/_ref) executed on the same B200, forward(input, z=z) on
     8192-ray chunks like render_realestate10k_traj.py:96; TF32 off (the parity-grade setting) and torch's
@@ -527,6 +578,12 @@ def main():
         if world == 1:
             r = measure(ctx, "fp32", 1, 512, 128, args.steps, args.warmup, 0 if args.no_e2e else 5, with_clocks=True, seed_base=300)
             extra["c4_512_p128"] = {"workload": "512x512 target, 2 views, 128 samples, fp32 maps, 1 scene (BASELINE config 4)", **_public(r)}
+    # ---- strong scaling over a few scenes (N > 1): the scenes' rays are split across all ranks, the feature maps
+    # exist on rank 0 only and are broadcast one scene ahead (sharding.render_scenes_pipelined) -------------------
+    if world > 1 and not args.no_extra and (H, P, args.precision) == (256, 64, "fp32"):
+        st = strong_scaling(ctx, scenes_total=4, H=256, P=64, reps=max(3, args.steps))
+        if rank == 0:
+            extra["strong_4_scenes"] = st
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -78,6 +78,48 @@ def render_sharded(model, input, z, rank=None, world=None, gather=True, group=No
     return out
 
 
+def feature_shapes(b, n_view, H, W):
+    """Shapes of the encoder's maps for b scenes of n_view context images (reference models.py:178-188)."""
+    return [(b * n_view, 256, H // 4, W // 4), (b * n_view, 256, H // 2, W // 2), (b * n_view, 64, H, W)]
+
+
+def render_scenes_pipelined(model, scenes, src=0, group=None, gather=True, device=None):
+    """Strong scaling over FEW scenes: every scene's rays are split across all ranks, and its feature maps -
+    which exist only on rank ``src``, where the encoder ran - are broadcast once (north_star: "encoder features
+    broadcast once via NCCL over NVLink"), asynchronously and one scene ahead: the broadcast of scene k+1
+    overlaps the rendering of scene k.
+
+    ``scenes``: list of ``(input, z)``; ``z`` is the feature list on rank ``src`` and ``None`` elsewhere.
+    Returns (list of out dicts with gathered tiles, bytes broadcast per rank)."""
+    rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
+    if not scenes:
+        return [], 0
+
+    def start(k):
+        inp, z = scenes[k]
+        if z is None:
+            b, n = inp["context"]["rgb"].shape[:2]
+            H, W = inp["context"]["rgb"].shape[2:4]
+            ref = inp["query"]["uv"]
+            dev = device if device is not None else ref.device
+            z = [torch.empty(shp, dtype=torch.float32, device=dev) for shp in feature_shapes(b, n, H, W)]
+        works = [dist.broadcast(t, src=src, group=group, async_op=True) for t in z] if world > 1 else []
+        return z, works
+
+    outs, nbytes = [], 0
+    nxt = start(0)
+    for k in range(len(scenes)):
+        z, works = nxt
+        if k + 1 < len(scenes):
+            nxt = start(k + 1)                      # in flight while scene k renders
+        for w in works:
+            w.wait()                                # the compute stream waits for scene k's maps (no host block on NCCL)
+        nbytes += sum(t.numel() * t.element_size() for t in z) if world > 1 else 0
+        outs.append(render_sharded(model, scenes[k][0], z, rank=rank, world=world, gather=gather, group=group))
+    return outs, nbytes
+
+
 def average_gradients(model, group=None, average=True):
     """Gradient exchange of the data-parallel training step (reference ``average_gradients``,
     training.py:21-28: one all_reduce per parameter, divided by the world size).  Here every

@@ -157,3 +157,55 @@ def test_sync_model_flat_broadcast_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res), res
+
+
+class _FakeModel:
+    """model(input, z=z, ray_range=rng) stand-in: rgb depends on the ray index AND on the broadcast feature maps,
+    so a rank that rendered with stale / un-broadcast maps is caught."""
+    def __call__(self, inp, z=None, ray_range=None):
+        b, _, R, _ = inp["query"]["uv"].shape
+        total = b * R
+        out = _fake_render(total, b, R, ray_range)
+        tag = float(z[0].flatten()[0] + z[2].flatten()[-1])
+        lo, hi = ray_range
+        out["rgb"].view(total, 3)[lo:hi] += tag
+        return out
+
+
+def _pipeline_worker(rank, world, port, nscenes, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        b, n, H, R = 1, 2, 8, 23
+        scenes, want = [], []
+        for k in range(nscenes):
+            inp = {"context": {"rgb": torch.zeros(b, n, H, H, 3)}, "query": {"uv": torch.zeros(b, 1, R, 2)}}
+            z = [torch.full(s, float(k + 1)) for s in sharding.feature_shapes(b, n, H, H)] if rank == 0 else None
+            scenes.append((inp, z))
+            g = torch.arange(b * R, dtype=torch.float32)
+            want.append(torch.stack([g, 2 * g, -g], -1) + 2.0 * (k + 1))
+        outs, nbytes = sharding.render_scenes_pipelined(_FakeModel(), scenes, src=0)
+        ok = len(outs) == nscenes and nbytes == nscenes * sum(4 * torch.Size(s).numel() for s in sharding.feature_shapes(b, n, H, H))
+        for o, w in zip(outs, want):
+            ok &= torch.equal(o["rgb"].view(-1, 3), w)
+        q.put((rank, bool(ok), None))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nscenes", [(2, 3), (3, 1)])
+def test_pipelined_scene_broadcast_gloo(world, nscenes):
+    """Strong-scaling path: features live on rank 0 only, are broadcast one scene ahead, every rank renders its
+    ray range of every scene and the tiles are gathered."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pipeline_worker, args=(r, world, port, nscenes, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res), res
