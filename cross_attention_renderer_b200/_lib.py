@@ -32,7 +32,7 @@ class car_weights(C.Structure):
                 ("key2", car_mat), ("qry1", car_mat), ("qry2", car_mat), ("rep1_loc", car_mat),
                 ("rep1_g", car_mat), ("rep2", car_mat), ("enc_lat", car_mat), ("phi_in", car_mat),
                 ("phi_z", car_mat * 3), ("phi_fc0", car_mat * 3), ("phi_fc1", car_mat * 3),
-                ("phi_out", car_mat), ("kv_fold", car_mat), ("kv_fold64", car_mat)]
+                ("phi_out", car_mat), ("kv_fold", car_mat), ("kv_fold64", car_mat), ("rowb_fold", car_mat), ("phi_pack", car_mat)]
 
 
 class car_cameras(C.Structure):

@@ -347,6 +347,12 @@ int phi_stage_umma(const car_render_args &a, const Workspace &w, int g0, int g1,
   const int split3 = a.precision == CAR_PREC_FP32_3XBF16;
   const int nr = g1 - g0;
   StageScope sc(CAR_ST_PHI);
+  if (W.phi_pack.hi) {
+    // one persistent kernel (car_phi.cu); its z operand is already in pr_hi / pr_lo when the fused tail produced it
+    const bool tail = (a.use_fused & 1) && (a.use_fused & 2) && (a.P == 64 || a.P == 128);
+    if (!tail) launch_split_rows(w.zfin, CAR_C_LAT, w.pr_hi, split3 ? w.pr_lo : nullptr, nr, CAR_C_LAT, st);
+    return launch_phi_fused(a, g0, g1, w.pr_hi, split3 ? w.pr_lo : nullptr, w.overlap, st);
+  }
   uint16_t *c_hi = w.pr_hi, *z_hi = c_hi + (size_t)nr * 32, *x_hi = z_hi + (size_t)nr * 288, *n_hi = x_hi + (size_t)nr * 128;
   uint16_t *c_lo = w.pr_lo, *z_lo = c_lo + (size_t)nr * 32, *x_lo = z_lo + (size_t)nr * 288, *n_lo = x_lo + (size_t)nr * 128;
   if (!split3) c_lo = z_lo = x_lo = n_lo = nullptr;
@@ -397,10 +403,21 @@ int sample_stage_umma(const car_render_args &a, const Workspace &w, int g0, int 
     if ((rc = launch_fused_encode(a, g0, g1, w.geom, w.value, w.hid_hi, split3 ? w.hid_lo : nullptr, st))) return rc;
     if (tail) {
       // per-ray tail: K, Q1, attention round 1 | per-ray 288->128->128 | Q2, attention round 2
-      if ((rc = launch_tail(a, 0, g0, g1, w.geom, w.value, w.hid_hi, w.hid_lo, w.q1, w.zsum, nullptr, nullptr, st))) return rc;
-      gemm(w.zsum, CAR_C_LAT, W.enc_lat, w.g, 128, nr, epi(W.enc_lat.bias, 0), st);
-      gemm(w.g, 128, W.rep1_g, w.rowbias, 128, nr, epi(W.rep1_g.bias, 0), st);
-      if ((rc = launch_tail(a, 1, g0, g1, w.geom, w.value, nullptr, nullptr, w.q1, w.zsum, w.rowbias, w.zfin, st))) return rc;
+      // zsum also leaves phase A as bf16 hi(+lo) (in the colour MLP's operand scratch, free until phi runs): the
+      // per-ray row bias is then ONE tcgen05 GEMM with rep1_g o enc_lat folded (was two exact-fp32 SIMT GEMMs: 6.2 ms/step)
+      const bool fold = W.rowb_fold.hi != nullptr;
+      if ((rc = launch_tail(a, 0, g0, g1, w.geom, w.value, w.hid_hi, w.hid_lo, w.q1, w.zsum, nullptr, nullptr,
+                            fold ? w.pr_hi : nullptr, fold && split3 ? w.pr_lo : nullptr, st))) return rc;
+      if (fold) {
+        if ((rc = mm(w.pr_hi, w.pr_lo, CAR_C_LAT, W.rowb_fold, nr, epi(W.rowb_fold.bias, 0), out_f(w.rowbias, 128)))) return rc;
+      } else {
+        gemm(w.zsum, CAR_C_LAT, W.enc_lat, w.g, 128, nr, epi(W.enc_lat.bias, 0), st);
+        gemm(w.g, 128, W.rep1_g, w.rowbias, 128, nr, epi(W.rep1_g.bias, 0), st);
+      }
+      // phase B leaves z as fp32 (debug taps) and as bf16 hi(+lo): the z operand of the fused colour MLP
+      const bool zpk = W.phi_pack.hi != nullptr;
+      if ((rc = launch_tail(a, 1, g0, g1, w.geom, w.value, nullptr, nullptr, w.q1, w.zsum, w.rowbias, w.zfin,
+                            zpk ? w.pr_hi : nullptr, zpk && split3 ? w.pr_lo : nullptr, st))) return rc;
       return 0;
     }
   } else {

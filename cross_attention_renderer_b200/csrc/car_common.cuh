@@ -102,10 +102,14 @@ int launch_gemm_umma(const uint16_t *a_hi, const uint16_t *a_lo, int lda, const 
 int launch_fused_encode(const car_render_args &a, int g0, int g1, const float *geom, float *value,
                         uint16_t *kh_hi, uint16_t *kh_lo, cudaStream_t st);
 
+// ---- car_phi.cu: colour MLP + mask / white fill in one persistent tcgen05 kernel -----------
+int launch_phi_fused(const car_render_args &a, int g0, int g1, const uint16_t *z_hi, const uint16_t *z_lo,
+                     const uint8_t *overlap, cudaStream_t st);
+
 // ---- car_tail.cu ------------------------------------------------------------------------
 int launch_tail(const car_render_args &a, int phase, int g0, int g1, const float *geom, const float *value,
                 const uint16_t *kh_hi, const uint16_t *kh_lo, float *q1, float *zsum, const float *rowbias,
-                float *zfin, cudaStream_t st);
+                float *zfin, uint16_t *zs_hi, uint16_t *zs_lo, cudaStream_t st);
 
 
 // ---- general branches (n_view 1 / 3, no_sample, no_latent_concat): car_general.cu ----------

@@ -46,6 +46,8 @@ struct TailParams {
   float *q1;                          // per ray [128 cols][128 rows] fp32 (column-major so that the one-row-per-lane
                                       // accesses coalesce): written in phase A, read in phase B
   float *zsum;                        // (rays,288)
+  uint16_t *zs_hi, *zs_lo;            // (rays,288) optional bf16 hi (+lo) copy of this phase's per-ray output: zsum (phase A, A operand
+                                      // of the row-bias GEMM) / z (phase B, operand of the fused colour MLP)
   const float *rowbias;               // (rays,128)  phase B
   float *zfin;                        // (rays,288)  phase B
   const float *bias_k2, *bias_q1, *bias_q2, *bias_r2;
@@ -532,10 +534,22 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
           z1 = (part[4 * CAR_C_LAT + c] + part[5 * CAR_C_LAT + c]) + (part[6 * CAR_C_LAT + c] + part[7 * CAR_C_LAT + c]);
         }
         if (PHASE == 0) {
-          p.zsum[(size_t)ray * CAR_C_LAT + c] = z0 + z1;                         // models.py:537-540
+          const float zz = z0 + z1;
+          p.zsum[(size_t)ray * CAR_C_LAT + c] = zz;                              // models.py:537-540
+          if (p.zs_hi) {
+            const __nv_bfloat16 hb = __float2bfloat16_rn(zz);
+            p.zs_hi[(size_t)ray * CAR_C_LAT + c] = __bfloat16_as_ushort(hb);
+            if (SPLIT == 3) p.zs_lo[(size_t)ray * CAR_C_LAT + c] = __bfloat16_as_ushort(__float2bfloat16_rn(zz - __bfloat162float(hb)));
+          }
         } else {
           const float zs = p.zsum[(size_t)ray * CAR_C_LAT + c];
-          p.zfin[(size_t)ray * CAR_C_LAT + c] = (z0 + zs) + (z1 + zs);           // models.py:561-564
+          const float zz = (z0 + zs) + (z1 + zs);                                // models.py:561-564
+          p.zfin[(size_t)ray * CAR_C_LAT + c] = zz;
+          if (p.zs_hi) {                                   // bf16 hi (+lo) copy: z operand of the fused colour MLP
+            const __nv_bfloat16 hb = __float2bfloat16_rn(zz);
+            p.zs_hi[(size_t)ray * CAR_C_LAT + c] = __bfloat16_as_ushort(hb);
+            if (SPLIT == 3) p.zs_lo[(size_t)ray * CAR_C_LAT + c] = __bfloat16_as_ushort(__float2bfloat16_rn(zz - __bfloat162float(hb)));
+          }
         }
       }
       asm volatile("bar.sync 3, 128;" ::: "memory");    // part[], vred[] reused by the next ray
@@ -558,7 +572,7 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
 // phase 1: needs rowbias, q1, zsum; writes zfin
 int launch_tail(const car_render_args &a, int phase, int g0, int g1, const float *geom, const float *value,
                 const uint16_t *kh_hi, const uint16_t *kh_lo, float *q1, float *zsum, const float *rowbias,
-                float *zfin, cudaStream_t st) {
+                float *zfin, uint16_t *zs_hi, uint16_t *zs_lo, cudaStream_t st) {
   const int split3 = a.precision == CAR_PREC_FP32_3XBF16;
   const car_weights &W = a.weights;
   if (a.P != 64 && a.P != 128) { set_error("tail kernel needs P == 64 or 128"); return -30; }
@@ -579,7 +593,7 @@ int launch_tail(const car_render_args &a, int phase, int g0, int g1, const float
   if (phase != 0) { tk_h = t0h; tk_l = t0l; }
   TailParams p;
   p.a = a; p.g0 = g0; p.g1 = g1; p.geom = geom; p.value = value; p.q1 = q1; p.zsum = zsum;
-  p.rowbias = rowbias; p.zfin = zfin;
+  p.rowbias = rowbias; p.zfin = zfin; p.zs_hi = zs_hi; p.zs_lo = zs_lo;
   p.stats = g_fused_stats ? g_fused_stats + 32 + phase * 16 : nullptr;
   p.bias_k2 = W.key2.bias; p.bias_q1 = W.qry1.bias; p.bias_q2 = W.qry2.bias; p.bias_r2 = W.rep2.bias;
   const int ops = split3 ? 2 : 1;

@@ -89,11 +89,22 @@ class PackedWeights:
                     src = v * 576 + c * 192 + h * 96 + j * 32
                     perm[dst:dst + 32] = torch.arange(src, src + 32)
         self.m["kv_fold64"] = P(fold.float()[:, perm.to(fold.device)], bfold.float())
+        # colour MLP: all ten matrices along K in 64-column blocks (include/car_b200.h, car_weights::phi_pack)
+        pad = lambda w_, k_: torch.nn.functional.pad(w_, (0, k_ - w_.shape[1]))
+        parts = [pad(self.m["phi_in"].f32, 64)]
+        for i in range(3):
+            parts += [pad(self.m[f"phi_z{i}"].f32, 320), self.m[f"phi_fc0{i}"].f32, self.m[f"phi_fc1{i}"].f32]
+        self.m["phi_pack"] = P(torch.cat(parts, dim=1), None)
+        # per-ray row bias of the round-2 query MLP: query_repeat_embed[:, :128] o encode_latent (float64 product)
+        wg = rep[:, :128].double()
+        wel = g("encode_latent.weight").reshape(128, 288).double()
+        self.m["rowb_fold"] = P((wg @ wel).float(),
+                                (wg @ g("encode_latent.bias").double() + g("query_repeat_embed.bias").double()).float())
 
     def c_struct(self):
         w = _lib.car_weights()
         for name in ("enc1", "enc2", "value", "key1", "key2", "qry1", "qry2", "rep1_loc",
-                     "rep1_g", "rep2", "enc_lat", "phi_in", "phi_out", "kv_fold", "kv_fold64"):
+                     "rep1_g", "rep2", "enc_lat", "phi_in", "phi_out", "kv_fold", "kv_fold64", "rowb_fold", "phi_pack"):
             setattr(w, name, self.m[name].c_struct())
         for i in range(3):
             w.phi_z[i] = self.m[f"phi_z{i}"].c_struct()
@@ -164,7 +175,7 @@ class PackedGrads:
     def __init__(self, pw):
         self.g = {}
         for name, m in pw.m.items():
-            if name in ("kv_fold", "kv_fold64"):
+            if name in ("kv_fold", "kv_fold64", "rowb_fold", "phi_pack"):
                 continue
             w = torch.zeros_like(m.f32)
             b = None if m.bias is None else torch.zeros_like(m.bias)

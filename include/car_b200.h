@@ -95,6 +95,14 @@ typedef struct car_weights {
    * (c = q / 3, j = q % 3), lane half h, i < 32:  column v*576 + q*64 + h*32 + i  holds kv_fold column
    * v*576 + c*192 + h*96 + j*32 + i.  Same bias.  hi == NULL: the kernel falls back to 32-wide stages. */
   car_mat kv_fold64;
+  /* query_repeat_embed[:, :128] composed with encode_latent (Conv1d 288 -> 128, no non-linearity between them,
+   * models.py:548-553): the per-ray row bias of the round-2 query MLP in ONE 128 x 288 matrix,
+   * W = rep1_g @ enc_lat, bias = rep1_g @ b_enc_lat + b_query_repeat_embed.  Used by the fused-tail path. */
+  car_mat rowb_fold;
+  /* The ten colour-MLP matrices side by side along K (zero padded to 64-column blocks) for the fused phi kernel:
+   * [lin_in 64 | lin_z0 320 | fc_0[0] 128 | fc_1[0] 128 | lin_z1 320 | fc_0[1] 128 | fc_1[1] 128 | lin_z2 320 | ...]:
+   * N=128 K=1792.  Biases are read from phi_in / phi_z / phi_fc0 / phi_fc1; lin_out from phi_out.f32. */
+  car_mat phi_pack;
 } car_weights;
 
 /* ------------------------------------------------------------------------
