@@ -116,6 +116,8 @@ SYMBOLS = {
     "car_general_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
     "car_general_default_chunk_rays": (C.c_int, [C.c_int] * 3),
     "car_render_forward_general": (C.c_int, [C.POINTER(car_general_args)]),
+    "car_adam_step": (C.c_int, [c_fp, c_fp, c_fp, c_fp, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float,
+                                C.c_float, C.c_int, c_fp, c_fp]),
     "car_last_launch_count": (C.c_int, []),
     "car_profile_begin": (C.c_int, []),
     "car_profile_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]),

@@ -19,8 +19,10 @@
 //   warp 1  MMA issuer (tcgen05 cta_group::1, N = 128), accumulators in TMEM
 //   warps 2-5: one thread per sample row: TMEM -> bias/ReLU -> bf16 hi/lo A operand of the next
 //           GEMM (smem, 128B swizzle), row dots, softmax (shuffles + named barrier).
-//   warps 6-9: attention-weighted V sums of the ray whose softmax weights were just posted
-//           (double-buffered in smem), so V traffic overlaps the next ray's scores.
+//   warps 6-13: two groups of four V-sum warps; group g takes the rays whose softmax weights the row warps post in
+//           weight buffer g (alternate rays): attention-weighted V sums, at_wt / argmax / depth outputs.  The V sums
+//           are bound by the latency of their loads (24 x LDG.128 in flight per lane, 11.7 k cycles per ray against
+//           6.5 k for the row warps' MLP chain); two rays in flight per CTA double the bytes in flight.
 #include <math.h>
 
 #include "car_common.cuh"
@@ -35,7 +37,14 @@ using namespace ptx;
 
 // (An L2 prefetch of the next ray's V / Q1 with cp.async.bulk.prefetch.L2 doubled the DRAM reads of both
 // phases - ncu: 456 / 429 KB per ray against 291 / 220 KB algorithmic, L2 hit rate 13-20 % - and was removed.)
-constexpr int THREADS = 320;          // TMA, MMA, 4 row warps, 4 V-sum warps
+// TMA, MMA, 4 row warps, VG groups of 4 V-sum warps.  Two groups (448 threads, 128 registers per thread) pay in the
+// single-MMA bf16 mode (tail 77 -> 72.5 ms per step); in the hi+lo mode the row threads need their 168 registers -
+// at 128 their MLP chain grows from 14.1 k to 15.6 k cycles per ray and becomes the bottleneck (99 -> 109 ms) - so
+// that mode keeps one group (320 threads).
+template <int SPLIT> struct TailShape {
+  static constexpr int VG = SPLIT == 3 ? 1 : 2;
+  static constexpr int THREADS = (2 + 4 + 4 * VG) * 32;
+};
 constexpr int NBMAX = 3;
 
 struct TailParams {
@@ -91,13 +100,14 @@ __device__ __forceinline__ void rows_sync() { asm volatile("bar.sync 2, 128;" ::
 
 // PHASE 0 = A, 1 = B
 template <int SPLIT, int PHASE, int TT>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(TailShape<SPLIT>::THREADS, 1)
 k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUtensorMap tm_kh_lo,
        const __grid_constant__ CUtensorMap tm_w0_hi, const __grid_constant__ CUtensorMap tm_w0_lo,   // key2 (A only)
        const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_constant__ CUtensorMap tm_w1_lo,   // K=16 layer
        const __grid_constant__ CUtensorMap tm_w2_hi, const __grid_constant__ CUtensorMap tm_w2_lo,   // 128x128 layer
        TailParams p) {
   using C = TCfg<SPLIT>;
+  constexpr int VG = TailShape<SPLIT>::VG;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *at0 = smem;                                        // relu(key_map) tile (phase A)
@@ -106,10 +116,10 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
   uint8_t *at1 = at0 + (PHASE == 0 ? C::TILE : Q1_BYTES);     // local (first 32 B of each row) then the hidden tile
   uint8_t *bs = at1 + C::TILE;
   float *arow = reinterpret_cast<float *>(bs + (size_t)p.nb * C::B_STAGE);   // [2][128 TT] softmax weights
-  float *part = arow + 256 * TT;                                                    // [4 TT][288] V sums per 32-row chunk
-  float *red = part + 4 * TT * CAR_C_LAT;                                      // [32] scratch
-  float *vred = red + 32;                                                      // [32] scratch of the V warps
-  float *sbias = vred + 32;                                                    // [3][128] hidden / output / key biases
+  float *part_all = arow + 256 * TT;                                                // [2 groups][4 TT][288] V sums per 32-row chunk
+  float *red = part_all + 2 * 4 * TT * CAR_C_LAT;                              // [32] scratch
+  float *vred_all = red + 32;                                                  // [2 groups][32] scratch of the V warps
+  float *sbias = vred_all + 64;                                                // [3][128] hidden / output / key biases
   uint64_t *bars = reinterpret_cast<uint64_t *>(sbias + 3 * 128);
   uint64_t *kh_full = bars, *kh_empty = bars + 1, *loc_full = bars + 2, *hid_full = bars + 3;
   uint64_t *t_full = bars + 4, *k_full = bars + 5, *done = bars + 6;
@@ -429,15 +439,18 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
   } else {
     // =========================== V-sum warps (6..9) ===========================
     // per tile, warp vs sums rows [32 vs, 32 vs + 32): sum_i a[i] * V[i][0..288), lanes over float4 columns
-    const int vs = warp - 6;
+    const int vg = VG == 2 ? (warp - 6) >> 2 : 0;         // V group (VG == 2: = weight buffer = parity of the CTA's ray counter)
+    const int vs = (warp - 6) & 3;
     const int vt = vs * 32 + lane;
-    const bool rec = p.stats && blockIdx.x == 0 && vs == 0;
+    float *part = part_all + vg * (4 * TT * CAR_C_LAT);
+    float *vred = vred_all + vg * 32;
+    const bool rec = p.stats && blockIdx.x == 0 && vs == 0 && vg == 0;
     unsigned long long vacc[3] = {0, 0, 0};              // 0 wait weights 1 loads+fma 2 reduce+store
     const int l2 = lane < 8 ? 64 + lane : lane;          // third float4 column only exists for lanes 0..7
     const float m2 = lane < 8 ? 1.f : 0.f;
-    for (int ir = 0; ir < my_rays; ++ir) {
+    for (int ir = vg; ir < my_rays; ir += VG) {
       const int ray = (int)blockIdx.x + ir * (int)gridDim.x;
-      const uint32_t buf = (uint32_t)ir & 1;
+      const uint32_t buf = (uint32_t)ir & 1;           // VG == 2: == vg
       const int g = p.g0 + ray, scene = g / p.a.R, rr = g - scene * p.a.R;
       float w0 = 0.f, w1 = 0.f, w2 = 0.f;               // phase A: this warp's share of sum a * clamp(pt)
       long long tv = rec ? clock64() : 0;
@@ -503,7 +516,7 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_empty[buf]);        // weights of this buffer consumed
       if (rec) { vacc[1] += (unsigned long long)(clock64() - tv); tv = clock64(); }
-      asm volatile("bar.sync 3, 128;" ::: "memory");
+      if (vg == 0) asm volatile("bar.sync 3, 128;" ::: "memory"); else asm volatile("bar.sync 4, 128;" ::: "memory");
       if (PHASE == 0 && vt < 2) {
         // context c = rows [c P, (c+1) P) = chunks [2 TT c, 2 TT (c+1)) in row order: first maximum wins
         const int c = vt;
@@ -552,7 +565,7 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
           }
         }
       }
-      asm volatile("bar.sync 3, 128;" ::: "memory");    // part[], vred[] reused by the next ray
+      if (vg == 0) asm volatile("bar.sync 3, 128;" ::: "memory"); else asm volatile("bar.sync 4, 128;" ::: "memory");    // part[], vred[] reused by the next ray
       if (rec) vacc[2] += (unsigned long long)(clock64() - tv);
     }
     if (rec && lane == 0)
@@ -598,7 +611,7 @@ int launch_tail(const car_render_args &a, int phase, int g0, int g1, const float
   p.bias_k2 = W.key2.bias; p.bias_q1 = W.qry1.bias; p.bias_q2 = W.qry2.bias; p.bias_r2 = W.rep2.bias;
   const int ops = split3 ? 2 : 1;
   const size_t tile = 2 * 128 * 128 * ops, bstage = 128 * 128 * ops;
-  const size_t fixed = (phase == 0 ? 2 * tile : tile + 128 * 128 * 4) + (256 * TT + 4 * TT * CAR_C_LAT + 64 + 3 * 128) * 4 + (12 + 2 * NBMAX) * 8 + 16 + 512;
+  const size_t fixed = (phase == 0 ? 2 * tile : tile + 128 * 128 * 4) + (256 * TT + 2 * 4 * TT * CAR_C_LAT + 32 + 64 + 3 * 128) * 4 + (12 + 2 * NBMAX) * 8 + 16 + 1024;
   int nb = (int)((227 * 1024 - fixed) / bstage);
   if (nb > NBMAX) nb = NBMAX;
   if (nb < 2) { set_error("tail: not enough shared memory"); return -31; }
@@ -612,7 +625,7 @@ int launch_tail(const car_render_args &a, int phase, int g0, int g1, const float
   do {                                                                                                  \
     e = cudaFuncSetAttribute(k_tail<S, PH, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
     if (e == cudaSuccess)                                                                               \
-      k_tail<S, PH, T><<<grid, THREADS, smem, st>>>(tk_h, tk_l, t0h, t0l, t1h, t1l, t2h, t2l, p);        \
+      k_tail<S, PH, T><<<grid, TailShape<S>::THREADS, smem, st>>>(tk_h, tk_l, t0h, t0l, t1h, t1l, t2h, t2l, p); \
   } while (0)
 #define CAR_TAIL_T(S, PH) do { if (TT == 1) CAR_TAIL(S, PH, 1); else CAR_TAIL(S, PH, 2); } while (0)
   if (split3) { if (phase == 0) CAR_TAIL_T(3, 0); else CAR_TAIL_T(3, 1); }

@@ -19,16 +19,19 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import _common as C                                                   # noqa: E402
+from cross_attention_renderer_b200.optim import FlatAdam             # noqa: E402
 
 
 def multigpu_train(gpu, opt):
     dev = C.init_distributed(gpu, opt.gpus, opt.master_port)
     model = C.build_model(opt, dev)
-    optimizer = torch.optim.Adam(lr=opt.lr, params=model.parameters(), betas=(0.99, 0.999))
     if opt.checkpoint_path is not None:
         C.load_checkpoint(model, opt.checkpoint_path, allow_encoder_mismatch=opt.allow_encoder_mismatch)
     if opt.gpus > 1:
         C.sync_model(model)
+    # Adam(lr, betas=(0.99, 0.999)) of the reference (train_realestate10k.py:86) on one flat parameter buffer:
+    # one all-reduce, one clip scalar and one fused kernel per step (cross_attention_renderer_b200/optim.py)
+    optimizer = FlatAdam(model.parameters(), lr=opt.lr, betas=(0.99, 0.999))
     model.train()
     model.pixel_val_to_cpu = False
 
@@ -60,10 +63,8 @@ def multigpu_train(gpu, opt):
                       f"({time.time() - t0:.1f} s)", flush=True)
             optimizer.zero_grad()
             train_loss.backward()
-            if opt.gpus > 1:
-                C.sharding.average_gradients(model)                   # training.py:21-28,127-128
-            torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
-            optimizer.step()
+            # average_gradients + clip_grad_norm_(1.0) + Adam.step (training.py:21-28,127-136)
+            optimizer.step(max_grad_norm=1.0)
             total_steps += 1
             if opt.iters_til_ckpt and not total_steps % opt.iters_til_ckpt and gpu == 0:
                 C.save_checkpoint(model, optimizer,

@@ -274,6 +274,17 @@ size_t car_general_workspace_bytes(int n_view, int flags, int P, int chunk_rays)
 int car_general_default_chunk_rays(int n_view, int flags, int P);
 int car_render_forward_general(const car_general_args *args);
 
+/* ------------------------------------------------------------------------
+ * Optimiser step of the training loop (reference training.py:124-136: average_gradients, clip_grad_norm_(1.0),
+ * torch.optim.Adam.step with betas (0.99, 0.999), train_realestate10k.py:86) as ONE kernel over a flat fp32
+ * buffer holding every parameter (host side: cross_attention_renderer_b200/optim.py::FlatAdam).  Arithmetic =
+ * torch.optim.Adam (amsgrad off); `grad_scale` (device scalar, may be NULL) multiplies the gradient first: the
+ * clip coefficient and / or 1 / world_size.  `step` counts from 1.
+ * ---------------------------------------------------------------------- */
+int car_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, size_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int step, const float *grad_scale,
+                  void *stream);
+
 /* Number of kernels the last car_render_forward / car_render_backward on this thread launched. */
 int car_last_launch_count(void);
 
