@@ -9,8 +9,9 @@ Per scene: ``get_z`` once, then the whole 256x256 target in ONE ``forward`` call
 splits it into 9 ray chunks to bound activation memory (eval_realestate10k.py:144-159); here the
 chunking happens inside the library.  With ``--gpus N`` the rays of each scene are sharded across
 the ranks and the tiles all-gathered (the reference's ranks each render everything).  Prints the
-reference's ``elapsed`` and ``mse, psnr`` lines (LPIPS / SSIM need packages that are not present
-here and are skipped).
+reference's ``elapsed`` and ``mse, psnr, lpip, ssim`` lines (eval_realestate10k.py:199): SSIM is the
+restatement of the skimage call in ``cross_attention_renderer_b200/metrics.py``; LPIPS is computed when the
+``lpips`` package and its weights are importable and printed as ``nan`` otherwise.
 """
 import os
 import sys
@@ -21,6 +22,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import _common as C                                                   # noqa: E402
+from cross_attention_renderer_b200 import metrics                     # noqa: E402
 
 
 def multigpu_train(gpu, opt):
@@ -34,7 +36,11 @@ def multigpu_train(gpu, opt):
         raise RuntimeError("RealEstate10k frames are not available in this environment: pass --synthetic N")
     n_scenes = opt.synthetic if not opt.max_steps else min(opt.synthetic, opt.max_steps)
     H = opt.sidelength
-    mses, psnrs = [], []
+    mses, psnrs, lpips_list, ssims = [], [], [], []
+    loss_fn_alex = None
+    if metrics.lpips_available():
+        import lpips
+        loss_fn_alex = lpips.LPIPS(net="vgg").to(dev)                 # eval_realestate10k.py:107
     with torch.no_grad():
         for val_i in range(n_scenes):
             model_input, gt = C.synthetic_scene_batch(1, H, 10_000 + val_i, device=dev)
@@ -54,8 +60,17 @@ def multigpu_train(gpu, opt):
             mse, psnr = C.psnr_masked(rgb, target, valid_mask)
             mses.append(mse)
             psnrs.append(psnr)
+            # images as the reference scores them: [0, 1], invalid rays grey on both sides (:177-178)
+            rgb01 = ((rgb + 1) * 0.5) * valid_mask + 0.5 * (1 - valid_mask)
+            tgt01 = ((target + 1) * 0.5) * valid_mask + 0.5 * (1 - valid_mask)
+            if loss_fn_alex is not None:
+                lpips_list.append(float(loss_fn_alex(((rgb01.permute(2, 0, 1) - 0.5) * 2)[None],
+                                                     ((tgt01.permute(2, 0, 1) - 0.5) * 2)[None])))
+            else:
+                lpips_list.append(float("nan"))
+            ssims.append(metrics.ssim(rgb01, tgt01))                 # :195
             if gpu == 0:
-                print("mse, psnr", np.mean(mses), np.mean(psnrs), flush=True)
+                print("mse, psnr, lpip, ssim", np.mean(mses), np.mean(psnrs), np.mean(lpips_list), np.mean(ssims), flush=True)
     if opt.gpus > 1:
         torch.distributed.destroy_process_group()
     return float(np.mean(psnrs))

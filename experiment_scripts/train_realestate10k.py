@@ -20,6 +20,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import _common as C                                                   # noqa: E402
 from cross_attention_renderer_b200.optim import FlatAdam             # noqa: E402
+from cross_attention_renderer_b200.summaries import img_summaries    # noqa: E402
 
 
 def multigpu_train(gpu, opt):
@@ -41,6 +42,13 @@ def multigpu_train(gpu, opt):
         if os.path.exists(root):
             shutil.rmtree(root)                                       # training.py:61-63 (overwrite=True)
         os.makedirs(ckpt_dir)
+    writer = None
+    if gpu == 0:
+        try:
+            from torch.utils.tensorboard import SummaryWriter
+            writer = SummaryWriter(os.path.join(root, "summaries"))    # training.py:77
+        except Exception as exc:                                       # noqa: BLE001
+            print(f"tensorboard unavailable ({exc!r}): no summaries", flush=True)
     if not opt.synthetic:
         raise RuntimeError("RealEstate10k frames are not available in this environment: pass --synthetic N "
                            "(the reference loader is dataset/realestate10k_dataio.py)")
@@ -58,6 +66,19 @@ def multigpu_train(gpu, opt):
                 train_loss = train_loss + C.depth_variance_loss(model_output, opt.l2_coeff)
             if not total_steps % opt.steps_til_summary and gpu == 0:
                 C.save_checkpoint(model, optimizer, os.path.join(ckpt_dir, "model_current.pth"))
+                if writer is not None:
+                    # training.py:105-120,142-231: loss scalars + a full-image validation render with image summaries
+                    writer.add_scalar("img_loss", float(train_loss.detach()), total_steps)
+                    writer.add_scalar("total_at_entropy", C.attention_entropy(model_output["at_wt"]), total_steps)
+                    model.eval()
+                    with torch.no_grad():
+                        val_in, val_gt = C.synthetic_scene_batch(1, opt.sidelength, 900_000 + total_steps, device=dev)
+                        val_out = model(val_in)
+                        val_out["pixel_val"] = val_out["pixel_val"].cpu()
+                        img_summaries(model, val_in, val_gt, None, val_out, writer, total_steps, prefix="val_",
+                                      img_shape=(opt.sidelength, opt.sidelength), n_view=opt.views)
+                        writer.add_scalar("val_loss", float(C.image_loss(val_out, val_gt)), total_steps)
+                    model.train()
                 print(f"step {total_steps}: loss {float(train_loss.detach()):.5f} "
                       f"at_entropy {C.attention_entropy(model_output['at_wt']):.4f} "
                       f"({time.time() - t0:.1f} s)", flush=True)
@@ -74,6 +95,8 @@ def multigpu_train(gpu, opt):
         if opt.max_steps and total_steps >= opt.max_steps:
             break
     if gpu == 0:
+        if writer is not None:
+            writer.close()
         C.save_checkpoint(model, optimizer, os.path.join(ckpt_dir, "model_final.pth"))
         print(f"done: {total_steps} steps, final loss {float(train_loss.detach()):.5f}", flush=True)
     if opt.gpus > 1:
