@@ -28,21 +28,23 @@ class FlatAdam:
         assert all(p.device == dev and p.dtype == torch.float32 for p in self.params)
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.step_count = 0
-        n = sum(p.numel() for p in self.params)
-        self.flat = torch.empty(n, device=dev)
+        # every parameter starts on a 256-byte boundary of the flat buffer: the CUDA kernels read weights with
+        # 16-byte vector loads and TMA, and torch's own kernels pick vectorised paths by pointer alignment
+        ALIGN = 64                                                     # floats
+        self.offsets, n = [], 0
+        for p in self.params:
+            self.offsets.append(n)
+            n += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.flat = torch.zeros(n, device=dev)
         self.grad = torch.zeros(n, device=dev)
         self.exp_avg = torch.zeros(n, device=dev)
         self.exp_avg_sq = torch.zeros(n, device=dev)
         self.scale = torch.ones((), device=dev)
-        off = 0
-        self.offsets = []
-        for p in self.params:
+        for p, off in zip(self.params, self.offsets):
             k = p.numel()
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view_as(p)            # the parameter now lives in the flat buffer
             p.grad = self.grad[off:off + k].view_as(p)            # autograd accumulates into this view
-            self.offsets.append(off)
-            off += k
 
     def zero_grad(self):
         self.grad.zero_()

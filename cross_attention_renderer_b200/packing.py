@@ -24,14 +24,20 @@ def _split_bf16(w):
     return hi.contiguous(), lo.contiguous()
 
 
+def _aligned(t):
+    """The kernels read weights with 16-byte vector loads / TMA: a view into some larger buffer (e.g. a flat
+    optimiser buffer) at an odd offset is copied to a fresh allocation."""
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
 class PackedMat:
     def __init__(self, w, bias, k_pad=None):
         w = w.detach().float().reshape(w.shape[0], -1)
         if k_pad is not None and k_pad != w.shape[1]:
             w = torch.nn.functional.pad(w, (0, k_pad - w.shape[1]))
-        self.f32 = w.contiguous()
+        self.f32 = _aligned(w.contiguous())
         self.hi, self.lo = _split_bf16(self.f32)
-        self.bias = None if bias is None else bias.detach().float().contiguous()
+        self.bias = None if bias is None else _aligned(bias.detach().float().contiguous())
         self.N, self.K = self.f32.shape
 
     def c_struct(self):
