@@ -16,4 +16,6 @@ for prec in ${PRECS:-fp32 bf16}; do
     [ -f gpurun_out/r02_${k}_${prec}.ncu-rep ] && python scripts/ncu_summary.py gpurun_out/r02_${k}_${prec}.ncu-rep > gpurun_out/r02_ncu_${k}_${prec}.json
   done
 done
+# gpurun merges at most 64 MiB back: keep the fused-kernel reports (source page, stall reasons), drop the tail's
+rm -f gpurun_out/r02_tail_*.ncu-rep
 ls -la gpurun_out/*.ncu-rep
