@@ -28,6 +28,7 @@
 //           The H ring then pairs the two lane halves of one accumulator block in one stage, and F is read
 //           through a column-permuted copy (car_weights::kv_fold64) whose K order is the epilogue's.
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <type_traits>
@@ -450,21 +451,26 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
         if (lane == 0) mbar_arrive_cluster(a1_empty, leader_crank);
       }
       // ---- acc3 -> V (fp32) and relu(key pre-activation) (bf16 hi/lo) ----
-      // Staged through shared memory and written out row-contiguously: a direct store of the TMEM image
-      // (lane = row, 1152-byte row pitch) touches 32 different lines per instruction - 6.6 k L1 wavefronts per ray,
-      // more than the whole bilinear gather - and kept the epilogue warps busy for 16-23 k cycles per ray
-      // (profiles/r02_fused_stalls.txt).  The staging area is the H ring: it is idle from a3_full (every GEMM3 MMA
-      // of this ray has retired) until these same warps drain the next ray's acc1.
-      //   rounds 0..2: V columns [96 r, 96 r + 96) as three [64 rows x 32 fp32] boxes (128-byte swizzle)
-      //   round  3   : relu(key) as two [64 x 64 bf16] boxes (hi) [+ two (lo)]
-      // Accumulator column n of the pair tile lives at chunk e = n / 208, lane half (n % 208) / 104.
+      // A direct store of the TMEM image (lane = row, 1152-byte row pitch) touches 32 different lines per
+      // instruction - 6.6 k L1 wavefronts per ray, more than the whole bilinear gather.  Each warp therefore
+      // transposes its 32 rows x 32 columns blocks through a private 4 KB staging area (swizzled, conflict-free
+      // both ways) and writes them out with 8 lanes per 128-byte row piece: 4 full lines per store instruction,
+      // no CTA-wide barrier (a first version staged whole 96-column rounds with two 128-thread barriers each;
+      // a TMA-store version queued behind the weight loads in the SM's TMA unit: profiles/README.md).
+      // The staging area is the H ring: idle from a3_full (every GEMM3 MMA of this ray has retired) until these
+      // same warps drain the next ray's acc1 - one barrier at the end keeps a fast warp's H writes away from a
+      // slow warp's staging.
+      // Accumulator column n of the pair tile lives at chunk e = n / 208, lane half (n % 208) / 104; this warp
+      // holds rows [32 (sub & 1), +32) of the CTA and the columns of its lane half.
       timed_wait(a3_full, rq & 1, st, 2);
       tc_fence_after();
       const long long td0 = st ? clock64() : 0;
-      const int grow0 = (int)row_base(ray);
+      const size_t grow0 = row_base(ray) + (size_t)((sub & 1) * 32);       // first global row of this warp
+      uint8_t *wbuf = hs + sub * 4096;
       const uint32_t tc0_ = tlane + ACC3_COL, tc1_ = tlane + ACC3_COL + (uint32_t)(N3CH / 2);
-      // V columns [n0, n0 + CNT) from TMEM columns [tcol, tcol + CNT) of this lane -> staging box of round n0 / 96
-      auto stage_v = [&](uint32_t tcol, int n0, auto CNT_) {
+      auto wsw = [&](int r_, int c_) { return (uint32_t)(r_ * 128 + ((c_ ^ (r_ & 7)) * 16)); };
+      // CNT (32 / 16 / 8) V columns starting at accumulator column n0 (this lane's TMEM columns [tcol, tcol + CNT))
+      auto drain_v = [&](uint32_t tcol, int n0, auto CNT_) {
         constexpr int CNT = decltype(CNT_)::value;
         uint32_t r[CNT];
         if constexpr (CNT == 32) tmem_ld32(tcol, r);
@@ -473,15 +479,27 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < CNT; i += 4) {
-          const int n = n0 + i, rel = n % 96;
-          const float4 bb = *reinterpret_cast<const float4 *>(sbiasf + n);
-          const float4 o = make_float4(__uint_as_float(r[i]) + bb.x, __uint_as_float(r[i + 1]) + bb.y,
-                                       __uint_as_float(r[i + 2]) + bb.z, __uint_as_float(r[i + 3]) + bb.w);
-          *reinterpret_cast<float4 *>(hs + (rel >> 5) * 8192 + swz_offset<128>(row, (rel & 31) >> 2)) = o;
+          const float4 bb = *reinterpret_cast<const float4 *>(sbiasf + n0 + i);
+          *reinterpret_cast<float4 *>(wbuf + wsw(lane, i >> 2)) =
+              make_float4(__uint_as_float(r[i]) + bb.x, __uint_as_float(r[i + 1]) + bb.y,
+                          __uint_as_float(r[i + 2]) + bb.z, __uint_as_float(r[i + 3]) + bb.w);
         }
+        __syncwarp();
+        constexpr int CPR = CNT / 4, RPI = 32 / CPR;       // 16-byte chunks per row, rows per store instruction
+        if (valid) {
+          const int cj = lane % CPR, r0 = lane / CPR;
+#pragma unroll
+          for (int i = 0; i < 32 / RPI; ++i) {
+            const int rr = r0 + RPI * i;
+            *reinterpret_cast<float4 *>(p.value + (grow0 + rr) * CAR_C_LAT + n0 + cj * 4) =
+                *reinterpret_cast<const float4 *>(wbuf + wsw(rr, cj));
+          }
+        }
+        __syncwarp();
       };
-      // relu(key) columns [k0, k0 + CNT) (accumulator columns 288 + k) -> bf16 hi (+lo) staging boxes
-      auto stage_k = [&](uint32_t tcol, int k0, auto CNT_) {
+      // CNT relu(key) columns starting at key column k0 (accumulator column 288 + k0): bf16 hi in chunks [0, CNT/8),
+      // lo in chunks [4, 4 + CNT/8) of the staging row
+      auto drain_k = [&](uint32_t tcol, int k0, auto CNT_) {
         constexpr int CNT = decltype(CNT_)::value;
         uint32_t r[CNT];
         if constexpr (CNT == 32) tmem_ld32(tcol, r);
@@ -490,75 +508,54 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < CNT; i += 8) {
-          const int k = k0 + i;
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            split2<SPLIT == 3>(fmaxf(__uint_as_float(r[i + 2 * j]) + sbiasf[CAR_C_LAT + k + 2 * j], 0.f),
-                               fmaxf(__uint_as_float(r[i + 2 * j + 1]) + sbiasf[CAR_C_LAT + k + 2 * j + 1], 0.f), hi[j], lo[j]);
-          const uint32_t off = (uint32_t)((k >> 6) * 8192) + swz_offset<128>(row, (k & 63) >> 3);
-          *reinterpret_cast<uint4 *>(hs + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          if (SPLIT == 3) *reinterpret_cast<uint4 *>(hs + 16384 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            split2<SPLIT == 3>(fmaxf(__uint_as_float(r[i + 2 * j]) + sbiasf[CAR_C_LAT + k0 + i + 2 * j], 0.f),
+                               fmaxf(__uint_as_float(r[i + 2 * j + 1]) + sbiasf[CAR_C_LAT + k0 + i + 2 * j + 1], 0.f), hi[j], lo[j]);
+          *reinterpret_cast<uint4 *>(wbuf + wsw(lane, i >> 3)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          if (SPLIT == 3) *reinterpret_cast<uint4 *>(wbuf + wsw(lane, 4 + (i >> 3))) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
+        __syncwarp();
+        constexpr int CPR = CNT / 8;                       // 16-byte chunks (8 bf16) per row and copy: 4 / 2 / 1
+        if (valid) {
+          // lanes: 8 slots per row (4 hi + 4 lo), 4 rows per instruction; slots beyond CPR idle
+          const int slot = lane & 7, r0 = lane >> 3, cj = slot & 3;
+          const bool is_lo = slot >= 4;
+          if (cj < CPR && (SPLIT == 3 || !is_lo)) {
+            uint16_t *dstb = is_lo ? p.kh_lo : p.kh_hi;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = r0 + 4 * i;
+              *reinterpret_cast<uint4 *>(dstb + (grow0 + rr) * 128 + k0 + cj * 8) =
+                  *reinterpret_cast<const uint4 *>(wbuf + wsw(rr, slot));
+            }
+          }
+        }
+        __syncwarp();
       };
       using I8 = std::integral_constant<int, 8>;
       using I16 = std::integral_constant<int, 16>;
       using I32 = std::integral_constant<int, 32>;
-      // staging complete -> coalesced global stores by all four warps -> staging free again.  Thread t copies the
-      // 16-byte chunk t % 8 of rows t / 8 + 16 i: one store instruction covers 4 full 128-byte lines.
-      // (TMA bulk-tensor stores from the same staging boxes were measured first: they queue behind the weight
-      // loads of the B ring in the SM's TMA unit and the per-round wait for their smem reads cost as much as the
-      // uncoalesced stores had.)
-      const int et = (int)threadIdx.x - 64;                // 0..127 among the epilogue threads
-      auto flush = [&](int round) {
-        const long long tfl0 = st ? clock64() : 0;
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (valid) {
-          const int cj = et & 7, r0 = et >> 3;
-          if (round < 3) {
-            float *vbase = p.value + (size_t)grow0 * CAR_C_LAT + round * 96 + cj * 4;
-#pragma unroll
-            for (int b = 0; b < 3; ++b)
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int rr = r0 + 16 * i;
-                const float4 v4 = *reinterpret_cast<const float4 *>(hs + b * 8192 + swz_offset<128>(rr, cj));
-                *reinterpret_cast<float4 *>(vbase + (size_t)rr * CAR_C_LAT + b * 32) = v4;
-              }
-          } else {
-#pragma unroll
-            for (int b = 0; b < 2; ++b)
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int rr = r0 + 16 * i;
-                const size_t o = ((size_t)grow0 + rr) * 128 + b * 64 + cj * 8;
-                *reinterpret_cast<uint4 *>(p.kh_hi + o) = *reinterpret_cast<const uint4 *>(hs + b * 8192 + swz_offset<128>(rr, cj));
-                if (SPLIT == 3) *reinterpret_cast<uint4 *>(p.kh_lo + o) = *reinterpret_cast<const uint4 *>(hs + 16384 + b * 8192 + swz_offset<128>(rr, cj));
-              }
-          }
-        }
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (st) st[7] += (unsigned long long)(clock64() - tfl0);
-      };
-      // round 0: V [0, 96) = columns 0..95 of chunk 0, lower lane half
-      if (half == 0) { stage_v(tc0_, 0, I32{}); stage_v(tc0_ + 32, 32, I32{}); stage_v(tc0_ + 64, 64, I32{}); }
-      flush(0);
-      // round 1: V [96, 192) = chunk 0: lower half columns 96..103, upper half columns 0..87 (n = 104 + col)
-      if (half == 0) stage_v(tc0_ + 96, 96, I8{});
-      else { stage_v(tc0_, 104, I8{}); stage_v(tc0_ + 8, 112, I16{}); stage_v(tc0_ + 24, 128, I32{}); stage_v(tc0_ + 56, 160, I32{}); }
-      flush(1);
-      // round 2: V [192, 288) = chunk 0 upper half columns 88..103 (n = 192..207), chunk 1 lower half columns 0..79 (n = 208..287)
-      if (half == 1) stage_v(tc0_ + 88, 192, I16{});
-      else { stage_v(tc1_, 208, I16{}); stage_v(tc1_ + 16, 224, I32{}); stage_v(tc1_ + 48, 256, I32{}); }
-      flush(2);
-      // round 3: relu(key): chunk 1 lower half columns 80..103 (k = 0..23), upper half columns 0..103 (k = 24..127)
-      if (half == 0) { stage_k(tc1_ + 80, 0, I8{}); stage_k(tc1_ + 88, 8, I16{}); }
-      else { stage_k(tc1_, 24, I8{}); stage_k(tc1_ + 8, 32, I32{}); stage_k(tc1_ + 40, 64, I32{}); stage_k(tc1_ + 72, 96, I32{}); }
-      // acc3 has been read completely: hand it back before the last flush
+      // chunk 0: all V.  n = half * 104 + col
+      {
+        const int nb = half * (N3CH / 2);
+        drain_v(tc0_, nb, I32{}); drain_v(tc0_ + 32, nb + 32, I32{}); drain_v(tc0_ + 64, nb + 64, I32{}); drain_v(tc0_ + 96, nb + 96, I8{});
+      }
+      // chunk 1: lower lane half = V 208..287 (columns 0..79) then key 0..23; upper half = key 24..127
+      if (half == 0) {
+        drain_v(tc1_, 208, I32{}); drain_v(tc1_ + 32, 240, I32{}); drain_v(tc1_ + 64, 272, I16{});
+        drain_k(tc1_ + 80, 0, I16{}); drain_k(tc1_ + 96, 16, I8{});
+      } else {
+        drain_k(tc1_, 24, I32{}); drain_k(tc1_ + 32, 56, I32{}); drain_k(tc1_ + 64, 88, I32{}); drain_k(tc1_ + 96, 120, I8{});
+      }
+      // acc3 has been read completely: hand it back; then all four warps are done with the staging area
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(a3_empty, leader_crank);
-      flush(3);
+      { const long long tfl0 = st ? clock64() : 0;
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (st) st[7] += (unsigned long long)(clock64() - tfl0); }
       if (st) st[6] += (unsigned long long)(clock64() - td0);
 
     }
@@ -781,6 +778,15 @@ int launch_fused_encode(const car_render_args &a, int g0, int g1, const float *g
       at[0].id = cudaLaunchAttributeClusterDimension;                                                         \
       at[0].val.clusterDim.x = p.cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                  \
       cfg.attrs = at; cfg.numAttrs = 1;                                                                       \
+      /* persistent kernel: every cluster must be resident at once.  Clusters of 4 do not tile the GPCs as      \
+         densely as pairs do, so ask how many fit and launch exactly that many (the work split follows gridDim) */ \
+      int maxc = 0;                                                                                           \
+      if (cudaOccupancyMaxActiveClusters(&maxc, k_fused_encode<S, T, K>, &cfg) == cudaSuccess && maxc > 0 &&  \
+          maxc * p.cl < pairs * 2) {                                                                          \
+        pairs = maxc * (p.cl / 2);                                                                            \
+        cfg.gridDim = dim3(pairs * 2);                                                                        \
+      }                                                                                                       \
+      if (getenv("CAR_FUSED_VERBOSE")) fprintf(stderr, "fused encode: cluster %d, %d clusters fit, grid %d\n", p.cl, maxc, pairs * 2); \
       e = cudaLaunchKernelEx(&cfg, k_fused_encode<S, T, K>, t1h, t1l, tfh, tfl, p);                           \
     }                                                                                                         \
   } while (0)
