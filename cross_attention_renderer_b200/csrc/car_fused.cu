@@ -50,7 +50,8 @@ constexpr int N1 = 576, N1CH = 192, N1C = 3;      // GEMM1: 3 MMA chunks of 192
 constexpr int N3 = 416, N3CH = 208, N3C = 2;      // GEMM3: 2 MMA chunks of 208
 constexpr int ACC1_COL = 0, ACC3_COL = 288;
 constexpr int PRODUCER_WARPS = 8;
-constexpr int THREADS = (2 + 4 + PRODUCER_WARPS) * 32;   // 448
+constexpr int BASE_WARPS = 2 + 4 + PRODUCER_WARPS;       // TMA, MMA, 4 epilogue, 8 gather = 448 threads
+constexpr int A3_STAGE = 2048;                           // bytes of private staging per dedicated acc3-drain warp
 constexpr int MAXB = 6;
 
 struct TapEntry { int off[4]; float w[4]; };              // 32 bytes
@@ -99,6 +100,12 @@ template <int SPLIT, int KS_> struct Cfg {
   static constexpr int NH = KS == 64 ? 3 : (SPLIT == 3 ? 4 : 6);   // NH * A_STAGE >= 24 KB (32 KB with lo copies): acc3 staging
   static constexpr int NX = KS == 64 ? 6 : (SPLIT == 3 ? 6 : 8);
   static constexpr int H_ARRIVALS = KS == 64 ? 8 : 4;              // epilogue warps per H stage (x 2 CTAs)
+  // Experiment kept as a switch: four more warps (14..17) drain acc3, so that the acc1 drains of the next ray - which
+  // gate GEMM3 - never queue behind the 14 k-cycle acc3 drain.  Measured in bf16 mode: 359 vs 305 ms per step.
+  // Registers are allocated in units of 32 per thread, so 576 threads get 96 instead of 128 and the gather / acc1
+  // loops spill (1 - 1.4 KB per thread); a build capped at 112 registers does not launch with 576 threads.
+  static constexpr bool A3W = false;
+  static constexpr int THREADS = (BASE_WARPS + (A3W ? 4 : 0)) * 32;
   static_assert(SW == 64 || SW == 128, "KS must be 32 or 64");
   static_assert(NH * A_STAGE >= (SPLIT == 3 ? 32768 : 24576), "H ring too small to stage acc3");
   static_assert(W1_CHUNK % 1024 == 0 || SW == 64, "128-byte-swizzled chunks must start on 1 KB boundaries");
@@ -147,13 +154,15 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t 
   }
 }
 
+// registers are allocated per warp in units of 1024 (32 per thread): 128 per thread at 448 threads, 96 at 576
+// (a kernel compiled with __maxnreg__(112) does not launch with 576 threads)
 template <int SPLIT, typename FT, int KS>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(Cfg<SPLIT, KS>::THREADS, 1)
 k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_constant__ CUtensorMap tm_w1_lo,
                const __grid_constant__ CUtensorMap tm_f_hi, const __grid_constant__ CUtensorMap tm_f_lo,
                FusedParams p) {
   using C = Cfg<SPLIT, KS>;
-  constexpr int SW = C::SW, K1_STAGES = C::K1_STAGES, K3_STAGES = C::K3_STAGES;
+  constexpr int SW = C::SW, K1_STAGES = C::K1_STAGES, K3_STAGES = C::K3_STAGES, THREADS = C::THREADS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *xs = smem;                                       // NX x A_STAGE
@@ -171,6 +180,7 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
   uint64_t *a1_full = b_empty + MAXB, *a1_empty = a1_full + 1;
   uint64_t *a3_full = a1_empty + 1, *a3_empty = a3_full + 1;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a3_empty + 1);
+  uint8_t *a3stage = reinterpret_cast<uint8_t *>(tmem_slot + 4);            // [4 warps][A3_STAGE] (A3W only), 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // cluster = p.cl CTAs (2 or 4) = p.cl/2 CTA pairs.  A pair (consecutive cluster ranks) shares one
@@ -220,6 +230,117 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
   cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  // ---- acc3 -> V (fp32) and relu(key pre-activation) (bf16 hi/lo), one warp's 32 rows ----
+  // A direct store of the TMEM image (lane = row, 1152-byte row pitch) touches 32 different lines per instruction -
+  // 6.6 k L1 wavefronts per ray, more than the whole bilinear gather.  The warp therefore transposes its 32 rows in
+  // blocks of SRB / 4 columns through a private staging area of 32 x SRB bytes (swizzled, conflict-free both ways)
+  // and writes them out row-contiguously: with SRB = 128, 8 lanes per 128-byte row piece = 4 full lines per store
+  // instruction.  (A first version staged 96-column rounds with two 128-thread barriers each; a TMA-store version
+  // queued behind the weight loads in the SM's TMA unit: profiles/README.md.)
+  // Accumulator column n of the pair tile lives at chunk e = n / 208, lane half (n % 208) / 104; warp `sub` of a
+  // TMEM-lane quarter set holds rows [32 (sub & 1), +32) of the CTA and the columns of lane half sub >> 1.
+  auto drain_acc3 = [&](auto SRB_, int ray, bool valid, uint32_t rq, uint8_t *wbuf, unsigned long long *st_) {
+    constexpr int SRB = decltype(SRB_)::value;             // staging row bytes: 128 or 64
+    constexpr int MAXC = SRB / 4;                          // fp32 columns per block
+    const int sub = warp & 3, half = sub >> 1;
+    const uint32_t tlane = tmem_base + ((uint32_t)(sub * 32) << 16);
+    timed_wait(a3_full, rq & 1, st_, 2);
+    tc_fence_after();
+    const size_t grow0 = row_base(ray) + (size_t)((sub & 1) * 32);       // first global row of this warp
+    const uint32_t tc0_ = tlane + ACC3_COL, tc1_ = tlane + ACC3_COL + (uint32_t)(N3CH / 2);
+    auto wsw = [&](int r_, int c_) {
+      return (uint32_t)(r_ * SRB + ((c_ ^ (SRB == 128 ? (r_ & 7) : ((r_ >> 1) & 3))) * 16));
+    };
+    // CNT (32 / 16 / 8) V columns starting at accumulator column n0 (this lane's TMEM columns [tcol, tcol + CNT))
+    auto drain_v = [&](uint32_t tcol, int n0, auto CNT_) {
+      constexpr int CNT = decltype(CNT_)::value;
+      uint32_t r[CNT];
+      if constexpr (CNT == 32) tmem_ld32(tcol, r);
+      else if constexpr (CNT == 16) tmem_ld16(tcol, r);
+      else tmem_ld8(tcol, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < CNT; i += 4) {
+        const float4 bb = *reinterpret_cast<const float4 *>(sbiasf + n0 + i);
+        *reinterpret_cast<float4 *>(wbuf + wsw(lane, i >> 2)) =
+            make_float4(__uint_as_float(r[i]) + bb.x, __uint_as_float(r[i + 1]) + bb.y,
+                        __uint_as_float(r[i + 2]) + bb.z, __uint_as_float(r[i + 3]) + bb.w);
+      }
+      __syncwarp();
+      constexpr int CPR = CNT / 4, RPI = 32 / CPR;         // 16-byte chunks per row, rows per store instruction
+      if (valid) {
+        const int cj = lane % CPR, r0 = lane / CPR;
+#pragma unroll
+        for (int i = 0; i < 32 / RPI; ++i) {
+          const int rr = r0 + RPI * i;
+          *reinterpret_cast<float4 *>(p.value + (grow0 + rr) * CAR_C_LAT + n0 + cj * 4) =
+              *reinterpret_cast<const float4 *>(wbuf + wsw(rr, cj));
+        }
+      }
+      __syncwarp();
+    };
+    // CNT relu(key) columns starting at key column k0 (accumulator column 288 + k0): bf16 hi in the staging row's
+    // chunks [0, CNT / 8), lo in chunks [LO, LO + CNT / 8)
+    auto drain_k = [&](uint32_t tcol, int k0, auto CNT_) {
+      constexpr int CNT = decltype(CNT_)::value;
+      constexpr int SPR = SRB / 16, LO = SPR / 2;          // 16-byte slots per staging row; first lo slot
+      uint32_t r[CNT];
+      if constexpr (CNT == 32) tmem_ld32(tcol, r);
+      else if constexpr (CNT == 16) tmem_ld16(tcol, r);
+      else tmem_ld8(tcol, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < CNT; i += 8) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          split2<SPLIT == 3>(fmaxf(__uint_as_float(r[i + 2 * j]) + sbiasf[CAR_C_LAT + k0 + i + 2 * j], 0.f),
+                             fmaxf(__uint_as_float(r[i + 2 * j + 1]) + sbiasf[CAR_C_LAT + k0 + i + 2 * j + 1], 0.f), hi[j], lo[j]);
+        *reinterpret_cast<uint4 *>(wbuf + wsw(lane, i >> 3)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (SPLIT == 3) *reinterpret_cast<uint4 *>(wbuf + wsw(lane, LO + (i >> 3))) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      __syncwarp();
+      constexpr int CPR = CNT / 8;                         // 16-byte chunks (8 bf16) per row and copy
+      if (valid) {
+        // lanes: SPR slots per row (hi then lo), 32 / SPR rows per instruction; slots beyond CPR idle
+        const int slot = lane % SPR, r0 = lane / SPR, cj = slot % LO;
+        const bool is_lo = slot >= LO;
+        if (cj < CPR && (SPLIT == 3 || !is_lo)) {
+          uint16_t *dstb = is_lo ? p.kh_lo : p.kh_hi;
+#pragma unroll
+          for (int i = 0; i < SPR; ++i) {
+            const int rr = r0 + (32 / SPR) * i;
+            *reinterpret_cast<uint4 *>(dstb + (grow0 + rr) * 128 + k0 + cj * 8) =
+                *reinterpret_cast<const uint4 *>(wbuf + wsw(rr, slot));
+          }
+        }
+      }
+      __syncwarp();
+    };
+    // LEN columns as blocks of at most MAXC
+    auto span = [&](auto &&fn, uint32_t tcol, int n0, auto LEN_) {
+      constexpr int LEN = decltype(LEN_)::value, NFULL = LEN / MAXC, REM = LEN % MAXC;
+#pragma unroll
+      for (int i = 0; i < NFULL; ++i) fn(tcol + (uint32_t)(i * MAXC), n0 + i * MAXC, std::integral_constant<int, MAXC>{});
+      if constexpr (REM >= 16) fn(tcol + (uint32_t)(NFULL * MAXC), n0 + NFULL * MAXC, std::integral_constant<int, 16>{});
+      if constexpr (REM % 16 == 8) fn(tcol + (uint32_t)(NFULL * MAXC + (REM >= 16 ? 16 : 0)), n0 + NFULL * MAXC + (REM >= 16 ? 16 : 0),
+                                      std::integral_constant<int, 8>{});
+    };
+    // chunk 0: all V, n = half * 104 + col
+    span(drain_v, tc0_, half * (N3CH / 2), std::integral_constant<int, 104>{});
+    // chunk 1: lower lane half = V 208..287 (columns 0..79) then key 0..23; upper half = key 24..127
+    if (half == 0) {
+      span(drain_v, tc1_, 208, std::integral_constant<int, 80>{});
+      span(drain_k, tc1_ + 80, 0, std::integral_constant<int, 24>{});
+    } else {
+      span(drain_k, tc1_, 24, std::integral_constant<int, 104>{});
+    }
+    // acc3 has been read completely: hand it back
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(a3_empty, leader_crank);
+  };
 
   if (warp == 0) {
     // =========================== B-operand TMA producer ===========================
@@ -450,115 +571,21 @@ k_fused_encode(const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(a1_empty, leader_crank);
       }
-      // ---- acc3 -> V (fp32) and relu(key pre-activation) (bf16 hi/lo) ----
-      // A direct store of the TMEM image (lane = row, 1152-byte row pitch) touches 32 different lines per
-      // instruction - 6.6 k L1 wavefronts per ray, more than the whole bilinear gather.  Each warp therefore
-      // transposes its 32 rows x 32 columns blocks through a private 4 KB staging area (swizzled, conflict-free
-      // both ways) and writes them out with 8 lanes per 128-byte row piece: 4 full lines per store instruction,
-      // no CTA-wide barrier (a first version staged whole 96-column rounds with two 128-thread barriers each;
-      // a TMA-store version queued behind the weight loads in the SM's TMA unit: profiles/README.md).
-      // The staging area is the H ring: idle from a3_full (every GEMM3 MMA of this ray has retired) until these
-      // same warps drain the next ray's acc1 - one barrier at the end keeps a fast warp's H writes away from a
-      // slow warp's staging.
-      // Accumulator column n of the pair tile lives at chunk e = n / 208, lane half (n % 208) / 104; this warp
-      // holds rows [32 (sub & 1), +32) of the CTA and the columns of its lane half.
-      timed_wait(a3_full, rq & 1, st, 2);
-      tc_fence_after();
-      const long long td0 = st ? clock64() : 0;
-      const size_t grow0 = row_base(ray) + (size_t)((sub & 1) * 32);       // first global row of this warp
-      uint8_t *wbuf = hs + sub * 4096;
-      const uint32_t tc0_ = tlane + ACC3_COL, tc1_ = tlane + ACC3_COL + (uint32_t)(N3CH / 2);
-      auto wsw = [&](int r_, int c_) { return (uint32_t)(r_ * 128 + ((c_ ^ (r_ & 7)) * 16)); };
-      // CNT (32 / 16 / 8) V columns starting at accumulator column n0 (this lane's TMEM columns [tcol, tcol + CNT))
-      auto drain_v = [&](uint32_t tcol, int n0, auto CNT_) {
-        constexpr int CNT = decltype(CNT_)::value;
-        uint32_t r[CNT];
-        if constexpr (CNT == 32) tmem_ld32(tcol, r);
-        else if constexpr (CNT == 16) tmem_ld16(tcol, r);
-        else tmem_ld8(tcol, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < CNT; i += 4) {
-          const float4 bb = *reinterpret_cast<const float4 *>(sbiasf + n0 + i);
-          *reinterpret_cast<float4 *>(wbuf + wsw(lane, i >> 2)) =
-              make_float4(__uint_as_float(r[i]) + bb.x, __uint_as_float(r[i + 1]) + bb.y,
-                          __uint_as_float(r[i + 2]) + bb.z, __uint_as_float(r[i + 3]) + bb.w);
-        }
-        __syncwarp();
-        constexpr int CPR = CNT / 4, RPI = 32 / CPR;       // 16-byte chunks per row, rows per store instruction
-        if (valid) {
-          const int cj = lane % CPR, r0 = lane / CPR;
-#pragma unroll
-          for (int i = 0; i < 32 / RPI; ++i) {
-            const int rr = r0 + RPI * i;
-            *reinterpret_cast<float4 *>(p.value + (grow0 + rr) * CAR_C_LAT + n0 + cj * 4) =
-                *reinterpret_cast<const float4 *>(wbuf + wsw(rr, cj));
-          }
-        }
-        __syncwarp();
-      };
-      // CNT relu(key) columns starting at key column k0 (accumulator column 288 + k0): bf16 hi in chunks [0, CNT/8),
-      // lo in chunks [4, 4 + CNT/8) of the staging row
-      auto drain_k = [&](uint32_t tcol, int k0, auto CNT_) {
-        constexpr int CNT = decltype(CNT_)::value;
-        uint32_t r[CNT];
-        if constexpr (CNT == 32) tmem_ld32(tcol, r);
-        else if constexpr (CNT == 16) tmem_ld16(tcol, r);
-        else tmem_ld8(tcol, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < CNT; i += 8) {
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            split2<SPLIT == 3>(fmaxf(__uint_as_float(r[i + 2 * j]) + sbiasf[CAR_C_LAT + k0 + i + 2 * j], 0.f),
-                               fmaxf(__uint_as_float(r[i + 2 * j + 1]) + sbiasf[CAR_C_LAT + k0 + i + 2 * j + 1], 0.f), hi[j], lo[j]);
-          *reinterpret_cast<uint4 *>(wbuf + wsw(lane, i >> 3)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          if (SPLIT == 3) *reinterpret_cast<uint4 *>(wbuf + wsw(lane, 4 + (i >> 3))) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        }
-        __syncwarp();
-        constexpr int CPR = CNT / 8;                       // 16-byte chunks (8 bf16) per row and copy: 4 / 2 / 1
-        if (valid) {
-          // lanes: 8 slots per row (4 hi + 4 lo), 4 rows per instruction; slots beyond CPR idle
-          const int slot = lane & 7, r0 = lane >> 3, cj = slot & 3;
-          const bool is_lo = slot >= 4;
-          if (cj < CPR && (SPLIT == 3 || !is_lo)) {
-            uint16_t *dstb = is_lo ? p.kh_lo : p.kh_hi;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = r0 + 4 * i;
-              *reinterpret_cast<uint4 *>(dstb + (grow0 + rr) * 128 + k0 + cj * 8) =
-                  *reinterpret_cast<const uint4 *>(wbuf + wsw(rr, slot));
-            }
-          }
-        }
-        __syncwarp();
-      };
-      using I8 = std::integral_constant<int, 8>;
-      using I16 = std::integral_constant<int, 16>;
-      using I32 = std::integral_constant<int, 32>;
-      // chunk 0: all V.  n = half * 104 + col
-      {
-        const int nb = half * (N3CH / 2);
-        drain_v(tc0_, nb, I32{}); drain_v(tc0_ + 32, nb + 32, I32{}); drain_v(tc0_ + 64, nb + 64, I32{}); drain_v(tc0_ + 96, nb + 96, I8{});
-      }
-      // chunk 1: lower lane half = V 208..287 (columns 0..79) then key 0..23; upper half = key 24..127
-      if (half == 0) {
-        drain_v(tc1_, 208, I32{}); drain_v(tc1_ + 32, 240, I32{}); drain_v(tc1_ + 64, 272, I16{});
-        drain_k(tc1_ + 80, 0, I16{}); drain_k(tc1_ + 96, 16, I8{});
-      } else {
-        drain_k(tc1_, 24, I32{}); drain_k(tc1_ + 32, 56, I32{}); drain_k(tc1_ + 64, 88, I32{}); drain_k(tc1_ + 96, 120, I8{});
-      }
-      // acc3 has been read completely: hand it back; then all four warps are done with the staging area
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(a3_empty, leader_crank);
-      { const long long tfl0 = st ? clock64() : 0;
+      if (!C::A3W) {
+        // acc3 drain on these warps, staged in the H ring: it is idle from a3_full (every GEMM3 MMA of this ray has
+        // retired) until these same warps drain the next ray's acc1 - one barrier at the end keeps a fast warp's H
+        // writes away from a slow warp's staging.  (bf16 mode: warps 14..17 do this concurrently, see below.)
+        const long long td0 = st ? clock64() : 0;
+        drain_acc3(std::integral_constant<int, 128>{}, ray, valid, rq, hs + sub * 4096, st);
         asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (st) st[7] += (unsigned long long)(clock64() - tfl0); }
-      if (st) st[6] += (unsigned long long)(clock64() - td0);
+        if (st) st[6] += (unsigned long long)(clock64() - td0);
+      }
 
     }
+  } else if (C::A3W && warp >= BASE_WARPS) {
+    // =========================== acc3 drain warps (14..17, bf16 mode) ===========================
+    for (int itn = 0; itn < niter; ++itn)
+      drain_acc3(std::integral_constant<int, 64>{}, item_of(itn), valid_of(itn), (uint32_t)itn, a3stage + (warp & 3) * A3_STAGE, nullptr);
   } else {
     // =========================== gather producers (warps 6..13) ===========================
     // Four groups of two warps; group gi owns X-ring slot gi and produces the K-stages with
@@ -753,7 +780,7 @@ int launch_fused_encode(const car_render_args &a, int g0, int g1, const float *g
   const int nh = KS == 64 ? Cfg<1, 64>::NH : (split3 ? Cfg<3, 32>::NH : Cfg<1, 32>::NH);
   const int nx = KS == 64 ? Cfg<1, 64>::NX : (split3 ? Cfg<3, 32>::NX : Cfg<1, 32>::NX);
   const size_t fixed = (size_t)(nx + nh) * a_stage + 2 * (ROWS * 3 * 2 * sizeof(TapEntry) + ROWS * 8 * 4) + (N1 + N3) * 4 +
-                       (2 * NXMAX + 2 * NHMAX + 2 * MAXB + 4) * 8 + 16 + 1024;
+                       (2 * NXMAX + 2 * NHMAX + 2 * MAXB + 4) * 8 + 16 + 1024 + (KS == 64 && Cfg<1, 64>::A3W ? 4 * A3_STAGE : 0);
   int nb = (int)((227 * 1024 - fixed) / b_stage);
   if (nb > MAXB) nb = MAXB;
   if (nb < 2) { set_error("fused encode: not enough shared memory"); return -21; }
@@ -773,7 +800,7 @@ int launch_fused_encode(const car_render_args &a, int g0, int g1, const float *g
     e = cudaFuncSetAttribute(k_fused_encode<S, T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e == cudaSuccess) {                                                                                   \
       cudaLaunchConfig_t cfg = {};                                                                            \
-      cfg.gridDim = dim3(pairs * 2); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st; \
+      cfg.gridDim = dim3(pairs * 2); cfg.blockDim = dim3(Cfg<S, K>::THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st; \
       cudaLaunchAttribute at[1];                                                                              \
       at[0].id = cudaLaunchAttributeClusterDimension;                                                         \
       at[0].val.clusterDim.x = p.cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                  \
@@ -786,7 +813,12 @@ int launch_fused_encode(const car_render_args &a, int g0, int g1, const float *g
         pairs = maxc * (p.cl / 2);                                                                            \
         cfg.gridDim = dim3(pairs * 2);                                                                        \
       }                                                                                                       \
-      if (getenv("CAR_FUSED_VERBOSE")) fprintf(stderr, "fused encode: cluster %d, %d clusters fit, grid %d\n", p.cl, maxc, pairs * 2); \
+      if (getenv("CAR_FUSED_VERBOSE")) {                                                                      \
+        cudaFuncAttributes fa;                                                                                \
+        cudaFuncGetAttributes(&fa, k_fused_encode<S, T, K>);                                                  \
+        fprintf(stderr, "fused encode: cluster %d, %d clusters fit, grid %d, block %d, regs %d, maxThreadsPerBlock %d, smem %zu\n", \
+                p.cl, maxc, pairs * 2, (int)Cfg<S, K>::THREADS, fa.numRegs, fa.maxThreadsPerBlock, smem);     \
+      }                                                                                                       \
       e = cudaLaunchKernelEx(&cfg, k_fused_encode<S, T, K>, t1h, t1l, tfh, tfl, p);                           \
     }                                                                                                         \
   } while (0)
