@@ -45,7 +45,7 @@ template <int SPLIT> struct TailShape {
   static constexpr int VG = SPLIT == 3 ? 1 : 2;
   static constexpr int THREADS = (2 + 4 + 4 * VG) * 32;
 };
-constexpr int NBMAX = 3;
+constexpr int NBMAX = 5;
 
 struct TailParams {
   car_render_args a;                  // sizes, geometry outputs (at_wt, at_wt_max, depth_ray), cams.qinv
@@ -61,6 +61,10 @@ struct TailParams {
   float *zfin;                        // (rays,288)  phase B
   const float *bias_k2, *bias_q1, *bias_q2, *bias_r2;
   int nb;
+  int resident;                       // the phase's weight K-blocks (5 in phase A, 3 in phase B) all fit the B slots (bf16 mode):
+                                      // loaded once per CTA and kept instead of streamed once per tile.  Removes 30 % of the
+                                      // tail's L2 traffic; the kernel time did not change (72.3 ms per step: the per-ray
+                                      // dependent chain bounds it)
   unsigned long long *stats;         // optional [16]: row-thread cycle accounting of CTA 0 (see scripts/tail_stalls.py)
 };
 
@@ -183,6 +187,7 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
             tma_load_2d(at0 + C::TILE_HALF + C::KB_BYTES, &tm_kh_lo, kh_full, 64, r0);
           }
         }
+        if (p.resident && it > 0) continue;              // weights stay in their slots
         load_w(&tm_w1_hi, &tm_w1_lo, 0);                 // K = 16 layer: columns 16..63 are OOB zero fill
         if (PHASE == 0) {
           load_w(&tm_w0_hi, &tm_w0_lo, 0);
@@ -199,7 +204,7 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
     // one 64-wide K-block: `ksteps` MMAs (x3 in the split mode) of A(base a) x B(stage) into d
     auto gemm_kb = [&](uint32_t d, uint32_t a_addr, int ksteps, bool first) {
       const int s = bq % p.nb;
-      mbar_wait(&b_full[s], (bq / p.nb) & 1);
+      mbar_wait(&b_full[s], p.resident ? 0u : ((bq / p.nb) & 1));     // resident: completed once, never re-armed
       tc_fence_after();
       if (elect_one()) {
         const uint64_t da = make_desc<128>(a_addr);
@@ -215,7 +220,7 @@ k_tail(const __grid_constant__ CUtensorMap tm_kh_hi, const __grid_constant__ CUt
             umma_f16<1>(d, a, w + (uint64_t)(C::B_HALF >> 4), idesc, 1u);
           }
         }
-        umma_commit(&b_empty[s]);
+        if (!p.resident) umma_commit(&b_empty[s]);
       }
       __syncwarp();
       ++bq;
@@ -613,8 +618,11 @@ int launch_tail(const car_render_args &a, int phase, int g0, int g1, const float
   const size_t tile = 2 * 128 * 128 * ops, bstage = 128 * 128 * ops;
   const size_t fixed = (phase == 0 ? 2 * tile : tile + 128 * 128 * 4) + (256 * TT + 2 * 4 * TT * CAR_C_LAT + 32 + 64 + 3 * 128) * 4 + (12 + 2 * NBMAX) * 8 + 16 + 1024;
   int nb = (int)((227 * 1024 - fixed) / bstage);
+  const int per_tile = phase == 0 ? 5 : 3;              // weight K-blocks a tile consumes
   if (nb > NBMAX) nb = NBMAX;
   if (nb < 2) { set_error("tail: not enough shared memory"); return -31; }
+  p.resident = nb >= per_tile;
+  if (p.resident) nb = per_tile;                         // slot = block index
   p.nb = nb;
   const size_t smem = fixed + (size_t)nb * bstage;
   const int sms = sm_count();

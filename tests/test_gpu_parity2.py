@@ -176,25 +176,3 @@ def test_eval_mode_runs_the_inference_path_with_grad_enabled():
     assert out_t["rgb"].grad_fn is not None
     assert rel_err(out_t["rgb"].detach(), want) < 1e-4
 
-
-def test_host_batch_pipeline_matches_direct_calls():
-    """render_host_batches (upload of batch k+1 overlapped with the rendering of batch k) returns, batch by batch,
-    exactly what uploading and calling forward() does."""
-    from cross_attention_renderer_b200.pipeline import render_host_batches
-    b, H, Ht, P = 1, 64, 20, 64
-    sd = synthetic.make_state_dict(seed=51)
-    model = make_model(sd, P, H, precision="fp32", pixel_val_to_cpu=False)
-    pin = lambda t: t.pin_memory()
-    batches = []
-    for k in range(4):
-        inp = synthetic.make_inputs(b, H, Ht, seed=51 + k, mode="mixed")
-        inp = {a: {kk: pin(vv) for kk, vv in v.items()} for a, v in inp.items()}
-        batches.append((inp, [pin(t) for t in synthetic.make_features(b, H, seed=51 + k)]))
-    got = list(render_host_batches(model, batches, DEV))
-    assert len(got) == 4
-    for (inp, z), o in zip(batches, got):
-        with torch.no_grad():
-            ref = model(synthetic.to_device(inp, DEV), z=[t.to(DEV) for t in z])
-        for key in ("rgb", "valid_mask", "depth_ray"):
-            assert o[key].device.type == "cpu" and torch.equal(o[key], ref[key].cpu()), key
-    assert list(render_host_batches(model, [], DEV)) == []
