@@ -489,6 +489,56 @@ def strong_scaling(ctx, scenes_total, H, P, reps):
             "broadcast_gbs_if_serial": nb[0] / max(1e-9, (ms_b - ms_n) * 1e-3) / 1e9 if ms_b > ms_n else None}
 
 
+def general_branches(ctx, H, P, steps, warmup, precision="fp32"):
+    """The other forward branches (n_view 1 / 3, no_latent_concat) through the public
+    forward: one scene per step, inputs resident, device-timed; parity of a 256-ray slice against the oracle."""
+    from cross_attention_renderer_b200.models import CrossAttentionRenderer
+    dev = ctx["dev"]
+    out = {}
+    for name, nv, noconcat in (("n_view_1", 1, False), ("n_view_3", 3, False), ("no_latent_concat", 2, True)):
+        inp = synthetic.make_inputs(1, H, H, seed=500 + nv, n_ctx=nv)
+        z = synthetic.make_features(1, H, seed=500 + nv, n_view=nv)
+        sd = synthetic.make_state_dict(seed=0, n_view=nv, no_latent_concat=noconcat)
+        m = CrossAttentionRenderer(n_view=nv, npoints=P, no_latent_concat=noconcat, precision=precision).to(dev).eval()
+        m.load_state_dict(sd, strict=False)
+        m.H = m.W = H
+        m.pixel_val_to_cpu = False
+        inp_d, z_d = synthetic.to_device(inp, dev), [t.to(dev) for t in z]
+
+        def step():
+            m.release_features()
+            with torch.no_grad():
+                return m(inp_d, z=z_d)
+        for _ in range(warmup):
+            res = step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            res = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        launches = m.last_launch_count
+        # parity: the same inputs cut to 256 rays through the oracle restatement of this branch
+        from oracle import car_oracle as orc
+        sel = slice(0, 256)
+        sub = {"query": dict(inp["query"]), "context": inp["context"]}
+        sub["query"]["uv"] = inp["query"]["uv"][:, :, sel].contiguous()
+        fn = {1: orc.render_single_view, 2: orc.render, 3: orc.render_three_views}[nv]
+        with torch.no_grad():
+            ref = fn(sd, sub, z, H, H, P, **({"no_latent_concat": True} if noconcat else {}))
+        got = res["rgb"][:, :, sel].cpu()
+        rel = float((got - ref["rgb"]).abs().max() / ref["rgb"].abs().max().clamp_min(1e-12))
+        out[name] = {"workload": f"{H}x{H} target, n_view={nv}{', no_latent_concat' if noconcat else ''}, {P} samples, 1 scene, "
+                                 "car_render_forward_general (unfused; per-sample GEMMs: "
+                                 + ("tcgen05 hi+lo" if precision == "fp32" else "exact fp32 SIMT") + ")",
+                     "value": round(H * H / ms * 1e3, 1), "unit": "rays/s", "ms_per_step": round(ms, 3),
+                     "gpu_launches_per_step": launches,
+                     "parity": {"rays": 256, "rgb_rel_err_vs_oracle": rel, "ok": rel <= 1e-4}}
+    return out
+
+
 def reference_on_gpu(dev, H, P, rays=8192):
     """the unmodified reference (oracle/_ref) executed on the same B200, forward(input, z=z) on
     8192-ray chunks like render_realestate10k_traj.py:96; TF32 off (the parity-grade setting) and torch's
@@ -591,6 +641,7 @@ def main():
         if world == 1:
             r = measure(ctx, "fp32", 1, 512, 128, args.steps, args.warmup, 0 if args.no_e2e else 5, with_clocks=True, seed_base=300)
             extra["c4_512_p128"] = {"workload": "512x512 target, 2 views, 128 samples, fp32 maps, 1 scene (BASELINE config 4)", **_public(r)}
+            extra["general_branches"] = general_branches(ctx, 256, 64, max(2, min(3, args.steps)), 2)
     # ---- strong scaling over a few scenes (N > 1): the scenes' rays are split across all ranks, the feature maps
     # exist on rank 0 only and are broadcast one scene ahead (sharding.render_scenes_pipelined) -------------------
     if world > 1 and not args.no_extra and (H, P, args.precision) == (256, 64, "fp32"):

@@ -73,7 +73,8 @@ class car_general_args(C.Structure):
                 ("weights", car_general_weights), ("cams", car_cameras), ("uv", c_fp), ("interval", c_fp),
                 ("rgb", c_fp), ("valid_mask", c_fp), ("depth_ray", c_fp), ("at_wt", c_fp), ("at_wt_max", c_fp),
                 ("pixel_val", c_fp), ("coords", c_fp), ("workspace", c_fp), ("workspace_bytes", C.c_size_t),
-                ("stream", c_fp), ("chunk_rays", C.c_int32), ("debug_interp", c_fp), ("debug_zfinal", c_fp)]
+                ("stream", c_fp), ("chunk_rays", C.c_int32), ("debug_interp", c_fp), ("debug_zfinal", c_fp),
+                ("precision", C.c_int32)]
 
 
 FLAG_NO_SAMPLE, FLAG_NO_LATENT_CONCAT = 1, 2

@@ -93,6 +93,7 @@ struct UmmaOut {
   const float *f32_add = nullptr;   // with GemmEpi::accumulate: fp32 [M][ldc] added to the product (may alias f32)
   uint16_t *hi, *lo;        // [M][ldc] bf16 split output or null
   int ldc;
+  int atomic = 0;           // weight-gradient form: f32 += product, contraction split over CTAs, fp32 atomics
 };
 int launch_gemm_umma(const uint16_t *a_hi, const uint16_t *a_lo, int lda, const uint16_t *w_hi,
                      const uint16_t *w_lo, int ldw, int M, int N, int K, int split3,

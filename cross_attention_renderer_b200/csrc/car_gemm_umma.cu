@@ -13,6 +13,13 @@
 //   warps 2..5  epilogue: tcgen05.ld 32x32b -> bias/ReLU -> fp32 and/or bf16 hi(+lo) stores
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA) and TMEM full/empty mbarriers
 // (MMA <-> epilogue), so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Backward-pass forms (car_backward.cu):
+//   data gradient    dA = dY · W        A operand = dY, "W" operand = W^T; the epilogue applies the ReLU
+//                                       subgradient mask (a saved fp32 activation) and / or accumulates
+//   weight gradient  dW += dY^T · A     both operands given transposed ([N][M] and [K][M]: the long row
+//                                       dimension becomes the contraction), split along it over `splits`
+//                                       work items per output tile, partial tiles added with fp32 atomics
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -32,6 +39,10 @@ struct UmmaParams {
   const float *bias, *row_bias;
   int rows_per_group, relu;            // relu: 0 none, 1 on every output, 2 only on the bf16 operand copy
   const float *add_src;                // optional fp32 [M][ldc] added before activation (may alias out_f32)
+  const float *mask;                   // optional fp32 [M][ldmask]: result = 0 where mask <= 0 (not together with add_src)
+  int ldmask;
+  int splits, kb_per;                  // split along K: work item = (tile, split); kb_per K blocks per split
+  int atomic;                          // out_f32 += result with atomics (split-K partial tiles)
   float *out_f32;
   uint16_t *out_hi, *out_lo;
   int ldc;
@@ -155,7 +166,7 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_n = p.N / p.BN;
   const int num_m = (p.M + BM - 1) / BM;
-  const int num_tiles = num_m * num_n;
+  const int num_tiles = num_m * num_n * p.splits;          // work items: split index fastest
   const int num_kb = (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -180,8 +191,9 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int m0 = (t / num_n) * BM, n0 = (t % num_n) * p.BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int tile = t / p.splits, kb0 = (t % p.splits) * p.kb_per, kb1 = min(num_kb, kb0 + p.kb_per);
+        int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * p.BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t *st = smem + (size_t)stage * stage_bytes;
           mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
@@ -204,7 +216,8 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         mbar_wait(&tempty[acc], acc_phase ^ 1);          // epilogue drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_stride);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = (t % p.splits) * p.kb_per, kb1 = min(num_kb, kb0 + p.kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
@@ -215,7 +228,7 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
           if (ksteps > BK / UMMA_K) ksteps = BK / UMMA_K;
           for (int k = 0; k < ksteps; ++k) {
             const uint32_t koff = (uint32_t)k * UMMA_K * 2;     // bytes inside the 128-byte swizzle row
-            const uint32_t first = (kb | k) ? 1u : 0u;
+            const uint32_t first = ((kb - kb0) | k) ? 1u : 0u;
             umma_f16(tmem_d, make_desc_sw128(sa + koff), make_desc_sw128(sw + koff), idesc, first);
             if (SPLIT == 3) {
               umma_f16(tmem_d, make_desc_sw128(sa_lo + koff), make_desc_sw128(sw + koff), idesc, 1u);
@@ -234,7 +247,8 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     const int sub = warp & 3;                            // TMEM sub-partition this warp may read
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      int m0 = (t / num_n) * BM, n0 = (t % num_n) * p.BN;
+      const int tile = t / p.splits;
+      int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * p.BN;
       mbar_wait(&tfull[acc], acc_phase);
       tcgen05_fence_after();
       const int row = m0 + sub * 32 + lane;
@@ -245,8 +259,9 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
       // in one batch BEFORE the block's math (and before the TMEM wait of the caller): consumed load by
       // load it cost one global round trip per 8 columns, 16 per tile, and dominated the small GEMMs.
       auto fetch_add = [&](float4 (&av)[8], int c0, int cnt) {
-        if (!p.add_src || row >= p.M) return;
-        const float4 *src = reinterpret_cast<const float4 *>(p.add_src + (size_t)row * p.ldc + n0 + c0);
+        if ((!p.add_src && !p.mask) || row >= p.M) return;
+        const float4 *src = p.add_src ? reinterpret_cast<const float4 *>(p.add_src + (size_t)row * p.ldc + n0 + c0)
+                                      : reinterpret_cast<const float4 *>(p.mask + (size_t)row * p.ldmask + n0 + c0);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           if (i * 4 < cnt) av[i] = src[i];
@@ -280,7 +295,16 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
           }
-          if (p.out_f32) {
+          if (p.mask && !p.add_src) {
+            const float4 a0 = av[i0 / 4], a1 = av[i0 / 4 + 1];
+            const float mk[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = mk[i] > 0.f ? v[i] : 0.f;
+          }
+          if (p.atomic) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) atomicAdd(p.out_f32 + o + i, v[i]);
+          } else if (p.out_f32) {
             *reinterpret_cast<float4 *>(p.out_f32 + o) = make_float4(v[0], v[1], v[2], v[3]);
             *reinterpret_cast<float4 *>(p.out_f32 + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
           }
@@ -410,10 +434,28 @@ int launch_gemm_umma(const uint16_t *a_hi, const uint16_t *a_lo, int lda, const 
   p.bias = epi.bias; p.row_bias = epi.row_bias; p.rows_per_group = epi.rows_per_group > 0 ? epi.rows_per_group : 1;
   p.relu = epi.relu_out;
   p.add_src = epi.accumulate ? out.f32_add : nullptr;
+  p.mask = epi.mask; p.ldmask = epi.ldmask;
+  if (p.mask && p.add_src) { set_error("gemm_umma: mask and accumulate cannot be combined"); return -15; }
+  if (p.mask && (epi.ldmask % 4)) { set_error("gemm_umma: ldmask %% 4"); return -15; }
+  // split along K (weight gradients: few output tiles, very long contraction): about two work items per SM
+  const int num_kb = (K + BK - 1) / BK;
+  const int out_tiles = ((M + BM - 1) / BM) * (N / BN);
+  int splits = 1;
+  if (out.atomic) {
+    splits = (2 * sm_count() + out_tiles - 1) / out_tiles;
+    if (splits > (num_kb + 3) / 4) splits = (num_kb + 3) / 4;     // at least 4 K blocks per item
+    if (splits < 1) splits = 1;
+    if (!out.f32 || out.hi || epi.bias || epi.row_bias || epi.relu_out || p.mask || p.add_src) {
+      set_error("gemm_umma: the atomic (split-K) form writes fp32 sums only"); return -15;
+    }
+  }
+  p.kb_per = (num_kb + splits - 1) / splits;
+  p.splits = (num_kb + p.kb_per - 1) / p.kb_per;          // no empty split
+  p.atomic = out.atomic;
   p.out_f32 = out.f32; p.out_hi = out.hi; p.out_lo = out.lo; p.ldc = out.ldc;
   size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
   const int sms = sm_count();
-  int tiles = ((M + BM - 1) / BM) * (N / BN);
+  int tiles = out_tiles * p.splits;
   int grid = tiles < sms ? tiles : sms;
   cudaError_t e;
   prof_pre(-1, st);

@@ -16,6 +16,8 @@ struct GenWs {
   RaySeg *seg; uint8_t *overlap;
   float *geom, *x, *h1, *interp, *value, *hid, *key, *q1, *q2;
   float *zsum, *g, *rowbias, *zfin, *c32, *px, *pnet, *rgb3;
+  // tensor-core precision: bf16 hi / lo operand copies
+  uint16_t *x_hi, *x_lo, *h1_hi, *h1_lo, *in_hi, *in_lo, *hid_hi, *hid_lo, *loc_hi, *loc_lo;
   size_t bytes;
 };
 
@@ -48,6 +50,16 @@ GenWs carve(char *base, const GenShape &gs, int P, int chunk) {
   w.px = (float *)take((size_t)chunk * 128 * 4);
   w.pnet = (float *)take((size_t)chunk * 128 * 4);
   w.rgb3 = (float *)take((size_t)chunk * 4 * 4);
+  // operand copies of the tensor-core precision (allocated unconditionally: one workspace size per configuration)
+  w.x_hi = (uint16_t *)take(rows * gs.parts * gs.xw * 2);
+  w.x_lo = (uint16_t *)take(rows * gs.parts * gs.xw * 2);
+  if (enc) { w.h1_hi = (uint16_t *)take(rows * gs.parts * CAR_C_FEAT * 2); w.h1_lo = (uint16_t *)take(rows * gs.parts * CAR_C_FEAT * 2); }
+  if (enc || merge) { w.in_hi = (uint16_t *)take(rows * gs.ci * 2); w.in_lo = (uint16_t *)take(rows * gs.ci * 2); }
+  else { w.in_hi = w.x_hi; w.in_lo = w.x_lo; }
+  w.hid_hi = (uint16_t *)take(rows * 128 * 2);
+  w.hid_lo = (uint16_t *)take(rows * 128 * 2);
+  w.loc_hi = (uint16_t *)take(rows * 16 * 2);
+  w.loc_lo = (uint16_t *)take(rows * 16 * 2);
   w.bytes = off;
   return w;
 }
@@ -60,7 +72,8 @@ GemmEpi epi(const float *bias, int relu_out, int relu_in = 0, int accumulate = 0
   return e;
 }
 
-int check_mat(const car_mat &m, int N, int K, const char *name) {
+int check_mat(const car_mat &m, int N, int K, const char *name, bool tc = false) {
+  if (tc && (!m.hi || !m.lo)) { set_error("general path: weight %s needs bf16 hi / lo copies for the tensor-core precision", name); return -11; }
   if (!m.f32 || m.N != N || m.K != K) { set_error("general path: weight %s must be fp32 [%d][%d] (got N=%d K=%d)", name, N, K, m.N, m.K); return -11; }
   return 0;
 }
@@ -110,12 +123,14 @@ int car_render_forward_general(const car_general_args *pa) {
   const car_general_weights &W = a.weights;
   const bool enc = gs.parts > 1, merge = gs.parts == 1 && gs.xw == CAR_K_ENC;
   int rc;
-  if (enc && ((rc = check_mat(W.enc1, CAR_C_FEAT, CAR_K_ENC, "enc1")) || (rc = check_mat(W.enc2, CAR_C_LAT, CAR_C_FEAT, "enc2")))) return rc;
-  if (merge && (rc = check_mat(W.merge, CAR_C_FEAT, CAR_K_ENC, "merge"))) return rc;
-  if ((rc = check_mat(W.value, gs.L, gs.ci, "value")) || (rc = check_mat(W.key1, 128, gs.ci, "key1")) ||
-      (rc = check_mat(W.key2, 128, 128, "key2")) || (rc = check_mat(W.qry1, 128, 16, "qry1")) || (rc = check_mat(W.qry2, 128, 128, "qry2")) ||
-      (rc = check_mat(W.rep1_loc, 128, 16, "rep1_loc")) || (rc = check_mat(W.rep1_g, 128, 128, "rep1_g")) ||
-      (rc = check_mat(W.rep2, 128, 128, "rep2")) || (rc = check_mat(W.enc_lat, 128, gs.L, "enc_lat")) ||
+  if (a.precision != CAR_PREC_FP32_SIMT && a.precision != CAR_PREC_FP32_3XBF16) { set_error("general path: precision %d (0 or 1)", a.precision); return -5; }
+  const bool tc = a.precision == CAR_PREC_FP32_3XBF16;
+  if (enc && ((rc = check_mat(W.enc1, CAR_C_FEAT, CAR_K_ENC, "enc1", tc)) || (rc = check_mat(W.enc2, CAR_C_LAT, CAR_C_FEAT, "enc2", tc)))) return rc;
+  if (merge && (rc = check_mat(W.merge, CAR_C_FEAT, CAR_K_ENC, "merge", tc))) return rc;
+  if ((rc = check_mat(W.value, gs.L, gs.ci, "value", tc)) || (rc = check_mat(W.key1, 128, gs.ci, "key1", tc)) ||
+      (rc = check_mat(W.key2, 128, 128, "key2", tc)) || (rc = check_mat(W.qry1, 128, 16, "qry1", tc)) || (rc = check_mat(W.qry2, 128, 128, "qry2", tc)) ||
+      (rc = check_mat(W.rep1_loc, 128, 16, "rep1_loc", tc)) || (rc = check_mat(W.rep1_g, 128, 128, "rep1_g")) ||
+      (rc = check_mat(W.rep2, 128, 128, "rep2", tc)) || (rc = check_mat(W.enc_lat, 128, gs.L, "enc_lat")) ||
       (rc = check_mat(W.phi_in, 128, 32, "phi_in")) || (rc = check_mat(W.phi_out, 3, 128, "phi_out"))) return rc;
   for (int i = 0; i < 3; ++i)
     if ((rc = check_mat(W.phi_z[i], 128, gs.L, "phi_z")) || (rc = check_mat(W.phi_fc0[i], 128, 128, "phi_fc0")) ||
@@ -137,6 +152,36 @@ int car_render_forward_general(const car_general_args *pa) {
     launch_sample_geometry_general(a, g0, g1, w.seg, w.geom, st);
     launch_gather_general(a, gs, g0, g1, w.geom, w.x, st);
     // per-sample feature stage
+    if (tc) {
+      // tcgen05 GEMMs (car_gemm_umma.cu), operands as bf16 hi + lo between the layers, fp32 where attention reads them
+      auto out_bf = [&](uint16_t *hi, uint16_t *lo, int ldc, float *f32 = nullptr) { UmmaOut o; o.f32 = f32; o.hi = hi; o.lo = lo; o.ldc = ldc; return o; };
+      auto out_f = [&](float *f32, int ldc) { UmmaOut o; o.f32 = f32; o.hi = nullptr; o.lo = nullptr; o.ldc = ldc; return o; };
+      auto mm = [&](const uint16_t *ah, const uint16_t *al, int lda, const car_mat &m, int M, const GemmEpi &e, const UmmaOut &o) {
+        return launch_gemm_umma(ah, al, lda, m.hi, m.lo, m.K, M, m.N, m.K, 1, e, o, st);
+      };
+      launch_split_rows(w.x, gs.xw, w.x_hi, w.x_lo, rows * gs.parts, gs.xw, st);
+      launch_split_rows(w.geom + GG_LOCAL, CAR_GG_STRIDE, w.loc_hi, w.loc_lo, rows, 16, st);
+      if (enc) {
+        { StageScope sc(CAR_ST_GEMM_ENC1);
+          if ((rc = mm(w.x_hi, w.x_lo, CAR_K_ENC, W.enc1, rows * gs.parts, epi(W.enc1.bias, 1), out_bf(w.h1_hi, w.h1_lo, CAR_C_FEAT)))) return rc; }
+        { StageScope sc(CAR_ST_GEMM_ENC2);
+          if ((rc = mm(w.h1_hi, w.h1_lo, CAR_C_FEAT, W.enc2, rows * gs.parts, epi(W.enc2.bias, 0),
+                       out_bf(w.in_hi, w.in_lo, CAR_C_LAT, a.debug_interp ? w.interp : nullptr)))) return rc; }
+      } else if (merge) {
+        StageScope sc(CAR_ST_GEMM_ENC1);
+        if ((rc = mm(w.x_hi, w.x_lo, CAR_K_ENC, W.merge, rows, epi(W.merge.bias, 0),
+                     out_bf(w.in_hi, w.in_lo, CAR_C_FEAT, a.debug_interp ? w.interp : nullptr)))) return rc;
+      }
+      if (a.debug_interp)
+        cudaMemcpyAsync(a.debug_interp + (size_t)(g0 - a.ray_begin) * gs.n * a.P * gs.ci, w.interp, (size_t)rows * gs.ci * 4,
+                        cudaMemcpyDeviceToDevice, st);
+      { StageScope sc(CAR_ST_GEMM_KV);
+        if ((rc = mm(w.in_hi, w.in_lo, gs.ci, W.value, rows, epi(W.value.bias, 0), out_f(w.value, gs.L)))) return rc;
+        if ((rc = mm(w.in_hi, w.in_lo, gs.ci, W.key1, rows, epi(W.key1.bias, 1), out_bf(w.hid_hi, w.hid_lo, 128)))) return rc; }
+      if ((rc = mm(w.hid_hi, w.hid_lo, 128, W.key2, rows, epi(W.key2.bias, 0), out_f(w.key, 128)))) return rc;
+      if ((rc = mm(w.loc_hi, w.loc_lo, 16, W.qry1, rows, epi(W.qry1.bias, 1), out_bf(w.hid_hi, w.hid_lo, 128)))) return rc;
+      if ((rc = mm(w.hid_hi, w.hid_lo, 128, W.qry2, rows, epi(W.qry2.bias, 0), out_f(w.q1, 128)))) return rc;
+    } else {
     if (enc) {
       // query_encode_latent (+ReLU) and query_encode_latent_2 on every part (models.py:333-342, 436-446): M = rows * parts;
       // the parts of a row land side by side = the part-major order of weights.value / key1
@@ -157,11 +202,20 @@ int car_render_forward_general(const car_general_args *pa) {
     gemm(w.hid, 128, W.key2, w.key, 128, rows, epi(W.key2.bias, 0), st);
     gemm(w.geom + GG_LOCAL, CAR_GG_STRIDE, W.qry1, w.hid, 128, rows, epi(W.qry1.bias, 1), st);    // :529
     gemm(w.hid, 128, W.qry2, w.q1, 128, rows, epi(W.qry2.bias, 0), st);
+    }
     launch_attention1_general(a, gs, g0, g1, w.key, w.q1, w.value, w.geom, w.zsum, st);           // :532-545, 573-594
     gemm(w.zsum, gs.L, W.enc_lat, w.g, 128, nr, epi(W.enc_lat.bias, 0), st);                      // :548
     gemm(w.g, 128, W.rep1_g, w.rowbias, 128, nr, epi(W.rep1_g.bias, 0), st);
-    gemm(w.geom + GG_LOCAL, CAR_GG_STRIDE, W.rep1_loc, w.hid, 128, rows, epi(nullptr, 1, 0, 0, w.rowbias, gs.n * a.P), st);
-    gemm(w.hid, 128, W.rep2, w.q2, 128, rows, epi(W.rep2.bias, 0), st);
+    if (tc) {
+      UmmaOut oh; oh.f32 = nullptr; oh.hi = w.hid_hi; oh.lo = w.hid_lo; oh.ldc = 128;
+      UmmaOut oq; oq.f32 = w.q2; oq.hi = nullptr; oq.lo = nullptr; oq.ldc = 128;
+      if ((rc = launch_gemm_umma(w.loc_hi, w.loc_lo, 16, W.rep1_loc.hi, W.rep1_loc.lo, 16, rows, 128, 16, 1,
+                                 epi(nullptr, 1, 0, 0, w.rowbias, gs.n * a.P), oh, st))) return rc;
+      if ((rc = launch_gemm_umma(w.hid_hi, w.hid_lo, 128, W.rep2.hi, W.rep2.lo, 128, rows, 128, 128, 1, epi(W.rep2.bias, 0), oq, st))) return rc;
+    } else {
+      gemm(w.geom + GG_LOCAL, CAR_GG_STRIDE, W.rep1_loc, w.hid, 128, rows, epi(nullptr, 1, 0, 0, w.rowbias, gs.n * a.P), st);
+      gemm(w.hid, 128, W.rep2, w.q2, 128, rows, epi(W.rep2.bias, 0), st);
+    }
     launch_attention2_general(a, gs, g0, g1, w.q2, w.q1, w.value, w.zsum, w.zfin, st);            // :555-565
     if (a.debug_zfinal)
       cudaMemcpyAsync(a.debug_zfinal + (size_t)(g0 - a.ray_begin) * gs.L, w.zfin, (size_t)nr * gs.L * 4, cudaMemcpyDeviceToDevice, st);

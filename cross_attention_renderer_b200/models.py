@@ -399,6 +399,9 @@ def _launch_general(self, cams, uv, interval, z, b, R, ray_range=None, debug_tap
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     a.stream = torch.cuda.current_stream(dev).cuda_stream
     a.chunk_rays = chunk
+    # "fp32": per-sample GEMMs on tcgen05 with hi + lo bf16 operands; "fp32_simt": exact fp32; "bf16" has no
+    # single-MMA kernels on these branches and runs the (more accurate) hi + lo ones
+    a.precision = _lib.PREC_FP32_SIMT if self.precision == "fp32_simt" else _lib.PRECISIONS["fp32"]
     if debug_taps is not None:
         rows = (g1 - g0) * n * P
         ci = 576 if (self.no_latent_concat or n == 1) else 288 * n

@@ -226,8 +226,8 @@ int car_unpack_features(const float *nhwc, float *nchw, int bn, int C, int h, in
  *   n_view = 2 with CAR_FLAG_NO_SAMPLE          volumetric line instead of the clipped epipolar segment
  *                                               (geometry.py:165-187)
  *   n_view = 2 with CAR_FLAG_NO_LATENT_CONCAT   raw 576-channel features, no per-sample encoder (:476-477)
- * Same stages as car_render_forward with a different gather fan-out; they run the exact-fp32 kernels
- * (car_mat::f32 only).  Rows are ((scene*R + ray)*n_view + ctx)*P + sample; outputs have b*n_view leading
+ * Same stages as car_render_forward with a different gather fan-out, unfused: exact-fp32 kernels, or
+ * (precision = CAR_PREC_FP32_3XBF16) the per-sample GEMMs on tcgen05.  Rows are ((scene*R + ray)*n_view + ctx)*P + sample; outputs have b*n_view leading
  * dimensions where the n_view = 2 path has b*2.
  * ---------------------------------------------------------------------- */
 enum { CAR_FLAG_NO_SAMPLE = 1, CAR_FLAG_NO_LATENT_CONCAT = 2 };
@@ -268,9 +268,11 @@ typedef struct car_general_args {
   int32_t chunk_rays;             /* 0 = car_general_default_chunk_rays                               */
   float *debug_interp;            /* optional (rows, Ci) dump of the per-sample features fed to latent_value / key_map */
   float *debug_zfinal;            /* optional (rays, L)                                               */
+  int32_t precision;              /* CAR_PREC_FP32_SIMT (exact fp32) or CAR_PREC_FP32_3XBF16: the per-sample GEMMs on
+                                     tcgen05 with hi+lo bf16 operands (car_mat::hi / lo); the per-ray layers stay fp32  */
 } car_general_args;
 
-size_t car_general_workspace_bytes(int n_view, int flags, int P, int chunk_rays);
+size_t car_general_workspace_bytes(int n_view, int flags, int P, int chunk_rays);   /* sized for either precision */
 int car_general_default_chunk_rays(int n_view, int flags, int P);
 int car_render_forward_general(const car_general_args *args);
 

@@ -22,7 +22,8 @@ def cpu(t):
 
 def make(sd, cfg):
     m = CrossAttentionRenderer(n_view=cfg["n_view"], npoints=cfg["P"], no_sample=cfg.get("no_sample", False),
-                               no_latent_concat=cfg.get("no_latent_concat", False)).to(DEV).eval()
+                               no_latent_concat=cfg.get("no_latent_concat", False),
+                               precision=cfg.get("precision")).to(DEV).eval()
     missing, unexpected = m.load_state_dict(sd, strict=False)
     assert not unexpected and not missing, (missing, unexpected)
     m.H = m.W = cfg["H"]
@@ -46,7 +47,7 @@ def run(m, inp, z, cams, P, no_sample):
     return out
 
 
-def compare(out, ref, n, H, exact_pixel_val=True):
+def compare(out, ref, n, H, exact_pixel_val=True, argmax_rtol=1e-4):
     assert torch.equal(cpu(out["valid_mask"]), ref["valid_mask"])
     pv, rpv = out["pixel_val"], ref["pixel_val"]
     if exact_pixel_val:
@@ -62,10 +63,12 @@ def compare(out, ref, n, H, exact_pixel_val=True):
     assert rel_err(cpu(out["rgb"]), ref["rgb"]) < 1e-4
     assert torch.allclose(cpu(out["at_wt"]), ref["at_wt"], rtol=2e-3, atol=1e-6)
     assert float((cpu(out["depth_ray"]) - ref["depth_ray"]).abs().max()) < 2e-3
+    # argmax: the index the kernel picked must hold a reference weight within argmax_rtol of the reference maximum
+    # (equal indices wherever the top two reference weights are further apart than that)
     aw = ref["at_wt"]
-    top2 = aw.topk(2, dim=-1).values
-    decided = (top2[..., 0] - top2[..., 1]) > 1e-4 * top2[..., 0]
-    assert torch.equal(cpu(out["at_wt_max"])[..., 0][decided], ref["at_wt_max"][..., 0][decided])
+    picked = aw.gather(-1, cpu(out["at_wt_max"]))[..., 0]
+    top = aw.max(dim=-1).values
+    assert bool((picked >= top * (1 - argmax_rtol)).all()), int((picked < top * (1 - argmax_rtol)).sum())
     assert out["at_wt"].shape[0] == out["coords"].shape[0] == out["pixel_val"].shape[0] == ref["at_wt"].shape[0]
 
 
@@ -88,9 +91,12 @@ BIG = {
 }
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp32_simt"])
 @pytest.mark.parametrize("name", list(BIG))
-def test_branch_matches_oracle(name):
-    cfg = BIG[name]
+def test_branch_matches_oracle(name, precision):
+    """Both GEMM back ends of car_render_forward_general: tcgen05 with hi + lo bf16 operands ("fp32", the
+    default) and the exact fp32 kernels ("fp32_simt")."""
+    cfg = dict(BIG[name], precision=precision)
     nv = cfg["n_view"]
     inp = synthetic.make_inputs(cfg["b"], cfg["H"], cfg["Ht"], seed=cfg["seed"], mode=cfg["mode"], n_ctx=nv)
     z = synthetic.make_features(cfg["b"], cfg["H"], seed=cfg["seed"], n_view=nv)
@@ -104,7 +110,8 @@ def test_branch_matches_oracle(name):
     out = run(m, inp, z, cams, cfg["P"], cfg.get("no_sample", False))
     # no_sample: the oracle evaluates the projection with plain torch fp32 ops, the kernel with separately
     # rounded IEEE ops in the same order: identical on the host; compare to 1e-6 to stay device-independent
-    compare(out, ref, nv, cfg["H"], exact_pixel_val=not cfg.get("no_sample", False))
+    compare(out, ref, nv, cfg["H"], exact_pixel_val=not cfg.get("no_sample", False),
+            argmax_rtol=1e-4 if precision == "fp32_simt" else 2e-3)       # hi+lo GEMMs: the at_wt tolerance
     vm = cpu(out["valid_mask"])[..., 0].bool()
     rgb = cpu(out["rgb"])[:, 0]
     assert torch.equal(rgb[~vm], torch.ones_like(rgb[~vm]))
