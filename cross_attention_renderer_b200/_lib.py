@@ -111,7 +111,7 @@ SYMBOLS = {
     "car_default_chunk_rays": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "car_render_forward": (C.c_int, [C.POINTER(car_render_args)]),
     "car_train_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
-    "car_backward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "car_backward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "car_render_backward": (C.c_int, [C.POINTER(car_backward_args)]),
     "car_unpack_features": (C.c_int, [c_fp, c_fp, C.c_int, C.c_int, C.c_int, C.c_int, c_fp]),
     "car_general_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
@@ -129,6 +129,7 @@ SYMBOLS = {
 TEST_SYMBOLS = {
     "car_mma_rate_test": (C.c_int, [C.c_int] * 7 + [c_fp, c_fp]),
     "car_gemm_pair_test": (C.c_int, [c_fp] * 7 + [C.c_int] * 8 + [c_fp]),
+    "car_tap_fetch_ab": (C.c_int, [c_fp, C.c_int, C.c_int, c_fp, c_fp, c_fp, C.c_int] + [C.c_int] * 5 + [c_fp, c_fp]),
 }
 
 _lib = None

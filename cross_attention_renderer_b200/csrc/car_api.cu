@@ -60,8 +60,10 @@ static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // use_fused: bit 0 fused gather+encode, bit 1 fused attention tail (effective only for tensor-core
 // precisions with P == 64); the unfused activations are then never allocated.
-// train: keep every activation the backward pass reads in its own buffer (fp32 SIMT path).
+// train: keep every activation the backward pass reads in its own fp32 buffer (exact-fp32 path, or the unfused
+// tensor-core path, which adds the bf16 operand copies between its layers).
 Workspace carve(char *base, int precision, int P, int chunk, int use_fused, int train) {
+  if (train) use_fused = 0;
   const bool fused = precision != CAR_PREC_FP32_SIMT && (use_fused & 1) && P % 64 == 0;
   const bool tail = fused && (use_fused & 2) && (P == 64 || P == 128);
   Workspace w;
@@ -78,7 +80,7 @@ Workspace carve(char *base, int precision, int P, int chunk, int use_fused, int 
     w.key = (float *)take(rows * 128 * 4);
     w.q2 = (float *)take(rows * 128 * 4);
   }
-  if (precision == CAR_PREC_FP32_SIMT) {
+  if (precision == CAR_PREC_FP32_SIMT || train) {
     w.x = (float *)take(rows * 2 * CAR_K_ENC * 4);
     w.h1 = (float *)take(rows * 2 * CAR_C_FEAT * 4);
     w.interp = (float *)take(rows * CAR_C_FEAT * 4);
@@ -88,7 +90,8 @@ Workspace carve(char *base, int precision, int P, int chunk, int use_fused, int 
       w.hid_r = (float *)take(rows * 128 * 4);
       w.att2 = (float *)take(rows * 4);
     }
-  } else {
+  }
+  if (precision != CAR_PREC_FP32_SIMT) {
     bool lo = precision == CAR_PREC_FP32_3XBF16;
     w.hid_hi = (uint16_t *)take(rows * 128 * 2);
     if (lo) w.hid_lo = (uint16_t *)take(rows * 128 * 2);
@@ -105,7 +108,7 @@ Workspace carve(char *base, int precision, int P, int chunk, int use_fused, int 
         w.h1_lo = (uint16_t *)take(rows * 2 * CAR_C_FEAT * 2);
         w.in_lo = (uint16_t *)take(rows * CAR_C_FEAT * 2);
       }
-      w.interp = (float *)take(rows * CAR_C_FEAT * 4);   // only filled when debug.interp is set
+      if (!train) w.interp = (float *)take(rows * CAR_C_FEAT * 4);   // only filled when debug.interp is set
     }
   }
   w.zsum = (float *)take((size_t)chunk * CAR_C_LAT * 4);
@@ -175,6 +178,7 @@ void sample_stage_simt(const car_render_args &a, const Workspace &w, int g0, int
 
 // ---- per-sample stage, tcgen05 ------------------------------------------------------------
 int sample_stage_umma(const car_render_args &a, const Workspace &w, int g0, int g1, cudaStream_t st);
+int sample_stage_train_umma(const car_render_args &a, const Workspace &w, int g0, int g1, cudaStream_t st);
 int phi_stage_umma(const car_render_args &a, const Workspace &w, int g0, int g1, cudaStream_t st);
 
 // ---- per-ray colour MLP (resnet_block_fc.py:132-168), always exact fp32 ------------------
@@ -294,7 +298,7 @@ int car_render_forward(const car_render_args *pa) {
   if (a.train) {
     // training mode: the whole ray range is one chunk and its activations stay in the workspace
     // for car_render_backward
-    if (a.precision != CAR_PREC_FP32_SIMT) { set_error("train=1 needs precision CAR_PREC_FP32_SIMT"); return -12; }
+    if (a.precision == CAR_PREC_BF16) { set_error("train=1 needs precision CAR_PREC_FP32_SIMT or CAR_PREC_FP32_3XBF16"); return -12; }
     if (a.feat_bf16) { set_error("train=1 needs fp32 feature maps"); return -12; }
     chunk = span;
     if (carve(nullptr, a.precision, a.P, chunk, 0, 1).bytes > a.workspace_bytes) {
@@ -317,6 +321,9 @@ int car_render_forward(const car_render_args *pa) {
     if (a.precision == CAR_PREC_FP32_SIMT) {
       sample_stage_simt(a, w, g0, g1, st);
       dump(a.debug.x, w.x, row_off, rows, 2 * CAR_K_ENC, st);
+    } else if (a.train) {
+      int rc = sample_stage_train_umma(a, w, g0, g1, st);
+      if (rc) return rc;
     } else {
       int rc = sample_stage_umma(a, w, g0, g1, st);
       if (rc) return rc;
@@ -328,7 +335,7 @@ int car_render_forward(const car_render_args *pa) {
     dump(a.debug.q1, w.q1, row_off, rows, 128, st);
     dump(a.debug.q2, w.q2, row_off, rows, 128, st);
     dump(a.debug.zfinal, w.zfin, (size_t)(g0 - a.ray_begin), (size_t)(g1 - g0), CAR_C_LAT, st);
-    if (a.precision == CAR_PREC_FP32_SIMT) phi_stage(a, w, g0, g1, st);
+    if (a.precision == CAR_PREC_FP32_SIMT || a.train) phi_stage(a, w, g0, g1, st);     // per-ray layers: exact fp32 in training
     else { int rc = phi_stage_umma(a, w, g0, g1, st); if (rc) return rc; }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("kernel launch failed: %s", cudaGetErrorString(e)); return (int)e; }
@@ -376,6 +383,41 @@ int phi_stage_umma(const car_render_args &a, const Workspace &w, int g0, int g1,
   }
   gemm(w.px, 128, W.phi_out, w.rgb3, 3, nr, epi(W.phi_out.bias, 0, 1, 0), st);       // N = 3: exact fp32
   launch_finalize(a, g0, g1, w.rgb3, w.overlap, st);
+  return 0;
+}
+
+// Training forward in the tensor-core precision: the dataflow of sample_stage_simt, every per-sample GEMM on tcgen05
+// with hi + lo bf16 operands; each epilogue writes the fp32 activation car_render_backward reads AND the operand copy
+// of the next layer.  The per-ray layers (M = rays) stay exact fp32.
+int sample_stage_train_umma(const car_render_args &a, const Workspace &w, int g0, int g1, cudaStream_t st) {
+  const car_weights &W = a.weights;
+  const int nr = g1 - g0, rows = nr * 2 * a.P;
+  int rc;
+  auto out = [&](float *f32, int ldc, uint16_t *hi = nullptr, uint16_t *lo = nullptr) {
+    UmmaOut o; o.f32 = f32; o.hi = hi; o.lo = lo; o.ldc = ldc; return o; };
+  auto mm = [&](const uint16_t *ah, const uint16_t *al, int lda, const car_mat &m, int M, const GemmEpi &e, const UmmaOut &o) {
+    return launch_gemm_umma(ah, al, lda, m.hi, m.lo, m.K, M, m.N, m.K, 1, e, o, st);
+  };
+  launch_gather(a, g0, g1, w.geom, w.x, nullptr, nullptr, st);
+  launch_split_rows(w.x, CAR_K_ENC, w.x_hi, w.x_lo, rows * 2, CAR_K_ENC, st);
+  launch_split_rows(w.geom + G_LOCAL, CAR_GEOM_STRIDE, w.loc_hi, w.loc_lo, rows, 16, st);
+  { StageScope sc(CAR_ST_GEMM_ENC1);
+    if ((rc = mm(w.x_hi, w.x_lo, CAR_K_ENC, W.enc1, rows * 2, epi(W.enc1.bias, 1), out(w.h1, CAR_C_FEAT, w.h1_hi, w.h1_lo)))) return rc; }
+  { StageScope sc(CAR_ST_GEMM_ENC2);
+    if ((rc = mm(w.h1_hi, w.h1_lo, CAR_C_FEAT, W.enc2, rows * 2, epi(W.enc2.bias, 0), out(w.interp, CAR_C_LAT, w.in_hi, w.in_lo)))) return rc; }
+  { StageScope sc(CAR_ST_GEMM_KV);
+    if ((rc = mm(w.in_hi, w.in_lo, CAR_C_FEAT, W.value, rows, epi(W.value.bias, 0), out(w.value, CAR_C_LAT)))) return rc;
+    if ((rc = mm(w.in_hi, w.in_lo, CAR_C_FEAT, W.key1, rows, epi(W.key1.bias, 1), out(w.hid, 128, w.hid_hi, w.hid_lo)))) return rc; }
+  if ((rc = mm(w.hid_hi, w.hid_lo, 128, W.key2, rows, epi(W.key2.bias, 0), out(w.key, 128)))) return rc;
+  if ((rc = mm(w.loc_hi, w.loc_lo, 16, W.qry1, rows, epi(W.qry1.bias, 1), out(w.hid_q, 128, w.hid_hi, w.hid_lo)))) return rc;
+  if ((rc = mm(w.hid_hi, w.hid_lo, 128, W.qry2, rows, epi(W.qry2.bias, 0), out(w.q1, 128)))) return rc;
+  launch_attention1(a, g0, g1, w.key, w.q1, w.value, w.geom, w.zsum, nullptr, st);
+  gemm(w.zsum, CAR_C_LAT, W.enc_lat, w.g, 128, nr, epi(W.enc_lat.bias, 0), st);
+  gemm(w.g, 128, W.rep1_g, w.rowbias, 128, nr, epi(W.rep1_g.bias, 0), st);
+  if ((rc = mm(w.loc_hi, w.loc_lo, 16, W.rep1_loc, rows, epi(nullptr, 1, 0, 0, w.rowbias, 2 * a.P),
+               out(w.hid_r, 128, w.hid_hi, w.hid_lo)))) return rc;
+  if ((rc = mm(w.hid_hi, w.hid_lo, 128, W.rep2, rows, epi(W.rep2.bias, 0), out(w.q2, 128)))) return rc;
+  launch_attention2(a, g0, g1, w.q2, w.q1, w.value, w.zsum, w.zfin, w.att2, st);
   return 0;
 }
 

@@ -14,10 +14,14 @@
 // ds = a * (da - sum(a * da)); clamp backward passes min <= x <= max.  Nothing upstream of
 // the sample coordinates has a gradient (pt / depth detached, models.py:327-328,516).
 //
-// All matrix products are exact fp32 (k_gemm_simt for the data gradients with transposed
-// weights, k_wgrad_simt for the weight gradients).
+// Matrix products: exact fp32 (k_gemm_simt for the data gradients with transposed weights, k_wgrad_simt for the
+// weight gradients), or - CAR_PREC_FP32_3XBF16 - the per-sample layers on tcgen05 (k_gemm_umma, hi + lo bf16
+// operands: data gradients with the ReLU mask in the epilogue, weight gradients split along the row dimension);
+// the per-ray layers (M = rays) stay exact fp32 either way.
 #include <math.h>
 #include <string.h>
+
+#include <cuda_bf16.h>
 
 #include "car_common.cuh"
 
@@ -198,6 +202,65 @@ k_rgb_bwd(car_render_args a, int g0, int nr, const float *__restrict__ d_rgb, co
   dx[(size_t)gl * 128 + c] = x3[(size_t)gl * 128 + c] > 0.f ? v : 0.f;
 }
 
+// fp32 rows -> the bf16 hi + lo operand copies the tcgen05 gradient GEMMs read: row-major ([M][W], tight; data
+// gradient) and / or transposed ([W][M]; weight gradient, the row dimension becomes the contraction), plus the
+// column sums (bias gradient).  64 rows x 32 columns per CTA.
+__global__ void __launch_bounds__(256)
+k_split_ops(const float *__restrict__ src, int ld, int M, int W, uint16_t *__restrict__ hi, uint16_t *__restrict__ lo,
+            uint16_t *__restrict__ hiT, uint16_t *__restrict__ loT, float *__restrict__ db) {
+  __shared__ uint32_t tile[32][65];                 // [column][row]: hi | lo << 16
+  __shared__ float csum[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 32, c = c0 + tx;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rl = ty + 8 * i, r = r0 + rl;
+    const bool in = r < M && c < W;
+    const float v = in ? src[(size_t)r * ld + c] : 0.f;
+    s += v;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    const uint32_t hb = __bfloat16_as_ushort(h), lb = __bfloat16_as_ushort(l);
+    tile[tx][rl] = hb | (lb << 16);
+    if (hi && in) { hi[(size_t)r * W + c] = (uint16_t)hb; lo[(size_t)r * W + c] = (uint16_t)lb; }
+  }
+  if (db) csum[ty][tx] = s;
+  __syncthreads();
+  if (db && ty == 0 && c < W) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += csum[j][tx];
+    atomicAdd(db + c, t);
+  }
+  if (hiT) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cl = ty + 8 * j, cc = c0 + cl;
+      if (cc >= W) continue;
+      const uint32_t p0 = tile[cl][2 * tx], p1 = tile[cl][2 * tx + 1];
+      const int r = r0 + 2 * tx;
+      const size_t o = (size_t)cc * M + r;
+      if (r + 1 < M) {                              // M is even: 4-byte aligned pair
+        *reinterpret_cast<uint32_t *>(hiT + o) = (p0 & 0xffffu) | (p1 << 16);
+        *reinterpret_cast<uint32_t *>(loT + o) = (p0 >> 16) | (p1 & 0xffff0000u);
+      } else if (r < M) {
+        hiT[o] = (uint16_t)(p0 & 0xffffu); loT[o] = (uint16_t)(p0 >> 16);
+      }
+    }
+  }
+}
+
+void launch_split_ops(const float *src, int ld, int M, int W, uint16_t *hi, uint16_t *lo, uint16_t *hiT, uint16_t *loT,
+                      float *db, cudaStream_t st) {
+  if (M <= 0 || W <= 0) return;
+  dim3 grid((M + 63) / 64, (W + 31) / 32);
+  prof_pre(-1, st);
+  k_split_ops<<<grid, 256, 0, st>>>(src, ld, M, W, hi, lo, hiT, loT, db);
+  prof_post(st);
+  count_launch();
+}
+
 // ---- backward workspace ------------------------------------------------------------------
 struct BwWs {
   // transposed weights [K][N]
@@ -209,10 +272,15 @@ struct BwWs {
   float *d_rgb3, *dx, *dnet, *d_zfin, *d_zsum, *drowbias, *dg;
   // per-sample gradients
   float *ds, *dq1, *dhid, *dv, *dinterp, *dh1, *dxin;
+  // tensor-core precision: bf16 hi / lo operand copies of the current gradient (row-major and transposed), of the
+  // current saved activation (transposed), of local_coords (transposed, used twice) and of the transposed weights
+  uint16_t *dy_hi, *dy_lo, *dyT_hi, *dyT_lo, *aT_hi, *aT_lo, *locT_hi, *locT_lo;
+  uint16_t *enc1T_hi, *enc1T_lo, *enc2T_hi, *enc2T_lo, *valueT_hi, *valueT_lo, *key1T_hi, *key1T_lo;
+  uint16_t *key2T_hi, *key2T_lo, *qry2T_hi, *qry2T_lo, *rep2T_hi, *rep2T_lo;
   size_t bytes;
 };
 
-BwWs carve_bw(char *base, int P, int rays) {
+BwWs carve_bw(char *base, int precision, int P, int rays) {
   BwWs w;
   memset(&w, 0, sizeof(w));
   size_t off = 0;
@@ -233,6 +301,21 @@ BwWs carve_bw(char *base, int P, int rays) {
   w.ds = take(rows * 128); w.dq1 = take(rows * 128); w.dhid = take(rows * 128);
   w.dv = take(rows * CAR_C_LAT); w.dinterp = take(rows * CAR_C_FEAT);
   w.dh1 = take(rows * 2 * CAR_C_FEAT); w.dxin = take(rows * 2 * CAR_C_FEAT);
+  if (precision == CAR_PREC_FP32_3XBF16) {
+    auto take16 = [&](size_t n) { return (uint16_t *)take((n + 1) / 2); };
+    const size_t big = rows * 2 * CAR_C_FEAT;
+    w.dy_hi = take16(big); w.dy_lo = take16(big); w.dyT_hi = take16(big); w.dyT_lo = take16(big);
+    w.aT_hi = take16(rows * 2 * CAR_K_ENC); w.aT_lo = take16(rows * 2 * CAR_K_ENC);
+    w.locT_hi = take16(rows * 16); w.locT_lo = take16(rows * 16);
+    const size_t F = CAR_C_FEAT, L = CAR_C_LAT;
+    w.enc1T_hi = take16(F * F); w.enc1T_lo = take16(F * F);
+    w.enc2T_hi = take16(F * L); w.enc2T_lo = take16(F * L);
+    w.valueT_hi = take16(F * L); w.valueT_lo = take16(F * L);
+    w.key1T_hi = take16(F * 128); w.key1T_lo = take16(F * 128);
+    w.key2T_hi = take16(128 * 128); w.key2T_lo = take16(128 * 128);
+    w.qry2T_hi = take16(128 * 128); w.qry2T_lo = take16(128 * 128);
+    w.rep2T_hi = take16(128 * 128); w.rep2T_lo = take16(128 * 128);
+  }
   w.bytes = off;
   return w;
 }
@@ -260,7 +343,7 @@ using namespace car;
 
 extern "C" {
 
-size_t car_backward_workspace_bytes(int P, int rays) { return carve_bw(nullptr, P, rays).bytes; }
+size_t car_backward_workspace_bytes(int precision, int P, int rays) { return carve_bw(nullptr, precision, P, rays).bytes; }
 
 int car_unpack_features(const float *nhwc, float *nchw, int bn, int C, int h, int w, void *stream) {
   if (!nchw || !nhwc || bn <= 0 || C <= 0 || h <= 0 || w <= 0) { set_error("car_unpack_features: bad argument"); return -1; }
@@ -276,19 +359,20 @@ int car_render_backward(const car_backward_args *pb) {
   const car_backward_args &b = *pb;
   const car_render_args &a = *b.fwd;
   if (b.abi_version != CAR_ABI_VERSION || a.abi_version != CAR_ABI_VERSION) { set_error("ABI version mismatch"); return -2; }
-  if (!a.train || a.precision != CAR_PREC_FP32_SIMT) { set_error("car_render_backward needs the arguments of a train=1 CAR_PREC_FP32_SIMT forward"); return -12; }
+  if (!a.train || a.precision == CAR_PREC_BF16) { set_error("car_render_backward needs the arguments of a train=1 forward (CAR_PREC_FP32_SIMT or CAR_PREC_FP32_3XBF16)"); return -12; }
+  const bool tc = a.precision == CAR_PREC_FP32_3XBF16;
   if (!b.d_rgb && !b.d_depth_ray) { set_error("car_render_backward: no cotangent given"); return -6; }
   if (!b.workspace) { set_error("car_render_backward: null workspace"); return -6; }
   const int g0 = a.ray_begin, g1 = a.ray_end, nr = g1 - g0;
   if (nr <= 0) return 0;
-  if (carve_bw(nullptr, a.P, nr).bytes > b.workspace_bytes) { set_error("backward workspace too small: %zu bytes", b.workspace_bytes); return -8; }
+  if (carve_bw(nullptr, a.precision, a.P, nr).bytes > b.workspace_bytes) { set_error("backward workspace too small: %zu bytes", b.workspace_bytes); return -8; }
   int dev_count = 0;
   if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) { set_error("no CUDA device (there is no CPU fallback)"); return -7; }
   const bool any_feat = b.d_feat[0] || b.d_feat[1] || b.d_feat[2];
   if (any_feat && !(b.d_feat[0] && b.d_feat[1] && b.d_feat[2])) { set_error("d_feat: give all three levels or none"); return -6; }
 
   const Workspace f = carve((char *)a.workspace, a.precision, a.P, nr, 0, 1);     // saved activations
-  const BwWs w = carve_bw((char *)b.workspace, a.P, nr);
+  const BwWs w = carve_bw((char *)b.workspace, a.precision, a.P, nr);
   const car_weights &W = a.weights;
   const car_weight_grads &G = b.grads;
   cudaStream_t st = (cudaStream_t)b.stream;
@@ -311,6 +395,38 @@ int car_render_backward(const car_backward_args *pb) {
     launch_transpose(W.phi_fc0[i].f32, 128, 128, 128, w.fc0T[i], st);
     launch_transpose(W.phi_fc1[i].f32, 128, 128, 128, w.fc1T[i], st);
   }
+
+  if (tc) {   // operand copies of the transposed weights the per-sample data gradients multiply by
+    launch_split_rows(w.enc1T, F, w.enc1T_hi, w.enc1T_lo, F, F, st);
+    launch_split_rows(w.enc2T, L, w.enc2T_hi, w.enc2T_lo, F, L, st);
+    launch_split_rows(w.valueT, L, w.valueT_hi, w.valueT_lo, F, L, st);
+    launch_split_rows(w.key1T, 128, w.key1T_hi, w.key1T_lo, F, 128, st);
+    launch_split_rows(w.key2T, 128, w.key2T_hi, w.key2T_lo, 128, 128, st);
+    launch_split_rows(w.qry2T, 128, w.qry2T_hi, w.qry2T_lo, 128, 128, st);
+    launch_split_rows(w.rep2T, 128, w.rep2T_hi, w.rep2T_lo, 128, 128, st);
+  }
+  // The per-sample layers (M = rows or 2*rows) in the tensor-core precision: every gradient GEMM runs on tcgen05
+  // (car_gemm_umma.cu) with hi + lo bf16 operands.  ops(): operand copies of the gradient dY that the layer's GEMMs read
+  // (+ its bias gradient); act(): transposed copy of the saved activation; wg(): dW += dY^T·A; dg(): dA = dY·W.
+  int rc = 0;
+  auto ops = [&](const float *dY, int ld, int M, int N, bool rowmajor, const car_mat_grad &g) {
+    launch_split_ops(dY, ld, M, N, rowmajor ? w.dy_hi : nullptr, rowmajor ? w.dy_lo : nullptr, g.w ? w.dyT_hi : nullptr,
+                     g.w ? w.dyT_lo : nullptr, g.w ? g.bias : nullptr, st);
+  };
+  auto act = [&](const float *A, int ld, int M, int K) { launch_split_ops(A, ld, M, K, nullptr, nullptr, w.aT_hi, w.aT_lo, nullptr, st); };
+  auto wg = [&](const uint16_t *aT_hi, const uint16_t *aT_lo, const car_mat_grad &g, int ldw, int M, int N, int K) {
+    if (!g.w || rc) return;
+    for (int k0 = 0; k0 < K && !rc; k0 += CAR_C_FEAT) {      // K = 592: the 576 feature columns, then the 16 others
+      const int kn = K - k0 < CAR_C_FEAT ? K - k0 : CAR_C_FEAT;
+      UmmaOut o; o.f32 = g.w + k0; o.hi = nullptr; o.lo = nullptr; o.ldc = ldw; o.atomic = 1;
+      rc = launch_gemm_umma(w.dyT_hi, w.dyT_lo, M, aT_hi + (size_t)k0 * M, aT_lo + (size_t)k0 * M, M, N, kn, M, 1, plain(), o, st);
+    }
+  };
+  auto dg = [&](const uint16_t *wT_hi, const uint16_t *wT_lo, int N, int K, float *dA, int lda, int M, const GemmEpi &e) {
+    if (rc) return;
+    UmmaOut o; o.f32 = dA; o.f32_add = e.accumulate ? dA : nullptr; o.hi = nullptr; o.lo = nullptr; o.ldc = lda;
+    rc = launch_gemm_umma(w.dy_hi, w.dy_lo, N, wT_hi, wT_lo, N, M, K, N, 1, e, o, st);
+  };
 
   // ---- colour MLP: recompute the layer inputs (resnet_block_fc.py:146-166), then go back ----
   {
@@ -345,9 +461,20 @@ int car_render_backward(const car_backward_args *pb) {
   // ---- attention round 2 and the repeat-query MLP (models.py:548-565) ----
   k_attn2_bwd<<<nr, BT, 0, st>>>(P, w.d_zfin, f.value, f.att2, f.q1, f.q2, w.ds, w.dq1, w.dv, w.d_zsum);
   count_launch();
-  wgrad(w.ds, 128, f.hid_r, 128, G.rep2, 128, rows, 128, 128, 0, st);
-  dgrad(w.ds, 128, w.rep2T, 128, 128, w.dhid, 128, rows, masked(f.hid_r, 128), st);
-  wgrad(w.dhid, 128, f.geom + G_LOCAL, CAR_GEOM_STRIDE, G.rep1_loc, 16, rows, 128, 16, 0, st);
+  if (tc) {
+    ops(w.ds, 128, rows, 128, true, G.rep2);
+    act(f.hid_r, 128, rows, 128);
+    wg(w.aT_hi, w.aT_lo, G.rep2, 128, rows, 128, 128);
+    dg(w.rep2T_hi, w.rep2T_lo, 128, 128, w.dhid, 128, rows, masked(f.hid_r, 128));
+    ops(w.dhid, 128, rows, 128, false, G.rep1_loc);
+    launch_split_ops(f.geom + G_LOCAL, CAR_GEOM_STRIDE, rows, 16, nullptr, nullptr, w.locT_hi, w.locT_lo, nullptr, st);
+    wg(w.locT_hi, w.locT_lo, G.rep1_loc, 16, rows, 128, 16);
+    if (rc) return rc;
+  } else {
+    wgrad(w.ds, 128, f.hid_r, 128, G.rep2, 128, rows, 128, 128, 0, st);
+    dgrad(w.ds, 128, w.rep2T, 128, 128, w.dhid, 128, rows, masked(f.hid_r, 128), st);
+    wgrad(w.dhid, 128, f.geom + G_LOCAL, CAR_GEOM_STRIDE, G.rep1_loc, 16, rows, 128, 16, 0, st);
+  }
   k_raysum128<<<nr, 128, 0, st>>>(w.dhid, 2 * P, w.drowbias);
   count_launch();
   wgrad(w.drowbias, 128, f.g, 128, G.rep1_g, 128, nr, 128, 128, 0, st);
@@ -358,25 +485,60 @@ int car_render_backward(const car_backward_args *pb) {
   // ---- attention round 1 + depth (models.py:532-545,577-594) ----
   k_attn1_bwd<<<nr, BT, 0, st>>>(a, g0, w.d_zsum, b.d_depth_ray, f.value, f.key, f.q1, f.geom, w.ds, w.dq1, w.dv);
   count_launch();
-  // geometric query  Q1 = query_embed_2(relu(query_embed(local)))   (:529)
-  wgrad(w.dq1, 128, f.hid_q, 128, G.qry2, 128, rows, 128, 128, 0, st);
-  dgrad(w.dq1, 128, w.qry2T, 128, 128, w.dhid, 128, rows, masked(f.hid_q, 128), st);
-  wgrad(w.dhid, 128, f.geom + G_LOCAL, CAR_GEOM_STRIDE, G.qry1, 16, rows, 128, 16, 0, st);
-  // key  K = key_map_2(relu(key_map(interp)))   (:491)
-  wgrad(w.ds, 128, f.hid, 128, G.key2, 128, rows, 128, 128, 0, st);
-  dgrad(w.ds, 128, w.key2T, 128, 128, w.dhid, 128, rows, masked(f.hid, 128), st);
-  wgrad(w.dhid, 128, f.interp, F, G.key1, F, rows, 128, F, 0, st);
-  wgrad(w.dv, L, f.interp, F, G.value, F, rows, L, F, 0, st);
-  dgrad(w.dhid, 128, w.key1T, 128, F, w.dinterp, F, rows, plain(), st);
-  dgrad(w.dv, L, w.valueT, L, F, w.dinterp, F, rows, accum(), st);
+  if (tc) {
+    // geometric query (:529)
+    ops(w.dq1, 128, rows, 128, true, G.qry2);
+    act(f.hid_q, 128, rows, 128);
+    wg(w.aT_hi, w.aT_lo, G.qry2, 128, rows, 128, 128);
+    dg(w.qry2T_hi, w.qry2T_lo, 128, 128, w.dhid, 128, rows, masked(f.hid_q, 128));
+    ops(w.dhid, 128, rows, 128, false, G.qry1);
+    wg(w.locT_hi, w.locT_lo, G.qry1, 16, rows, 128, 16);
+    // key (:491)
+    ops(w.ds, 128, rows, 128, true, G.key2);
+    act(f.hid, 128, rows, 128);
+    wg(w.aT_hi, w.aT_lo, G.key2, 128, rows, 128, 128);
+    dg(w.key2T_hi, w.key2T_lo, 128, 128, w.dhid, 128, rows, masked(f.hid, 128));
+    ops(w.dhid, 128, rows, 128, true, G.key1);
+    act(f.interp, F, rows, F);                                       // interp^T serves key_map and latent_value
+    wg(w.aT_hi, w.aT_lo, G.key1, F, rows, 128, F);
+    dg(w.key1T_hi, w.key1T_lo, 128, F, w.dinterp, F, rows, plain());
+    ops(w.dv, L, rows, L, true, G.value);
+    wg(w.aT_hi, w.aT_lo, G.value, F, rows, L, F);
+    dg(w.valueT_hi, w.valueT_lo, L, F, w.dinterp, F, rows, accum());
+    // per-view encoder MLP (models.py:333-342)
+    ops(w.dinterp, L, rows2, L, true, G.enc2);
+    act(f.h1, F, rows2, F);
+    wg(w.aT_hi, w.aT_lo, G.enc2, F, rows2, L, F);
+    dg(w.enc2T_hi, w.enc2T_lo, L, F, w.dh1, F, rows2, masked(f.h1, F));
+    ops(w.dh1, F, rows2, F, any_feat, G.enc1);
+    act(f.x, CAR_K_ENC, rows2, CAR_K_ENC);
+    wg(w.aT_hi, w.aT_lo, G.enc1, CAR_K_ENC, rows2, F, CAR_K_ENC);
+    if (any_feat) {
+      dg(w.enc1T_hi, w.enc1T_lo, F, F, w.dxin, F, rows2, plain());
+      if (!rc) launch_gather_backward(a, g0, g1, f.geom, w.dxin, b.d_feat, st);
+    }
+    if (rc) return rc;
+  } else {
+    // geometric query  Q1 = query_embed_2(relu(query_embed(local)))   (:529)
+    wgrad(w.dq1, 128, f.hid_q, 128, G.qry2, 128, rows, 128, 128, 0, st);
+    dgrad(w.dq1, 128, w.qry2T, 128, 128, w.dhid, 128, rows, masked(f.hid_q, 128), st);
+    wgrad(w.dhid, 128, f.geom + G_LOCAL, CAR_GEOM_STRIDE, G.qry1, 16, rows, 128, 16, 0, st);
+    // key  K = key_map_2(relu(key_map(interp)))   (:491)
+    wgrad(w.ds, 128, f.hid, 128, G.key2, 128, rows, 128, 128, 0, st);
+    dgrad(w.ds, 128, w.key2T, 128, 128, w.dhid, 128, rows, masked(f.hid, 128), st);
+    wgrad(w.dhid, 128, f.interp, F, G.key1, F, rows, 128, F, 0, st);
+    wgrad(w.dv, L, f.interp, F, G.value, F, rows, L, F, 0, st);
+    dgrad(w.dhid, 128, w.key1T, 128, F, w.dinterp, F, rows, plain(), st);
+    dgrad(w.dv, L, w.valueT, L, F, w.dinterp, F, rows, accum(), st);
 
-  // ---- per-view encoder MLP (models.py:333-342): rows*2 view-rows of 288 / 576 / 592 ----
-  wgrad(w.dinterp, L, f.h1, F, G.enc2, F, rows2, L, F, 0, st);
-  dgrad(w.dinterp, L, w.enc2T, L, F, w.dh1, F, rows2, masked(f.h1, F), st);
-  wgrad(w.dh1, F, f.x, CAR_K_ENC, G.enc1, CAR_K_ENC, rows2, F, CAR_K_ENC, 0, st);
-  if (any_feat) {
-    dgrad(w.dh1, F, w.enc1T, F, F, w.dxin, F, rows2, plain(), st);
-    launch_gather_backward(a, g0, g1, f.geom, w.dxin, b.d_feat, st);
+    // ---- per-view encoder MLP (models.py:333-342): rows*2 view-rows of 288 / 576 / 592 ----
+    wgrad(w.dinterp, L, f.h1, F, G.enc2, F, rows2, L, F, 0, st);
+    dgrad(w.dinterp, L, w.enc2T, L, F, w.dh1, F, rows2, masked(f.h1, F), st);
+    wgrad(w.dh1, F, f.x, CAR_K_ENC, G.enc1, CAR_K_ENC, rows2, F, CAR_K_ENC, 0, st);
+    if (any_feat) {
+      dgrad(w.dh1, F, w.enc1T, F, F, w.dxin, F, rows2, plain(), st);
+      launch_gather_backward(a, g0, g1, f.geom, w.dxin, b.d_feat, st);
+    }
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("backward kernel launch failed: %s", cudaGetErrorString(e)); return (int)e; }

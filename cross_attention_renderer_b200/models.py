@@ -238,7 +238,8 @@ class CrossAttentionRenderer(nn.Module):
         With autograd enabled and a weight or feature map that requires grad, the call goes
         through ``_RenderFunction`` (training-mode forward + ``car_render_backward``): ``rgb``
         and ``depth_ray`` are then differentiable like the reference's (training.py:92,125)."""
-        # The differentiable path is the TRAINING path: it runs the exact-fp32 unfused kernels on the
+        # The differentiable path is the TRAINING path: it runs the unfused kernels (per-sample GEMMs on tcgen05
+        # with hi + lo bf16 operands, or exact fp32 when precision == "fp32_simt") on the
         # whole ray range as one chunk with every activation resident (training.py:92 calls the module in
         # train mode on 192 rays per scene).  It is therefore gated on ``self.training``: a module in
         # eval() mode always runs the configured inference precision, grad mode or not, and its outputs
@@ -254,7 +255,7 @@ class CrossAttentionRenderer(nn.Module):
             or any(p.requires_grad for n, p in self.named_parameters() if n in HOT_PATH_PARAMS))
         if needs_grad:
             rays = (b * R) if ray_range is None else (ray_range[1] - ray_range[0])
-            need = _lib.load().car_train_workspace_bytes(_lib.PREC_FP32_SIMT, self.npoints, max(1, rays))
+            need = _lib.load().car_train_workspace_bytes(self._train_precision(), self.npoints, max(1, rays))
             free = torch.cuda.mem_get_info(z[0].device)[0] + torch.cuda.memory_reserved(z[0].device) \
                 - torch.cuda.memory_allocated(z[0].device)
             if need > free:
@@ -274,13 +275,19 @@ class CrossAttentionRenderer(nn.Module):
             out["pixel_val"] = out["pixel_val"].cpu()                   # models.py:570
         return out
 
+    def _train_precision(self):
+        """Arithmetic of the training forward / backward GEMMs: fp32-equivalent on the tensor cores (hi + lo bf16
+        operands, three MMAs per product) unless the module was built with precision="fp32_simt" (exact fp32).
+        There is no single-bf16 training mode: "bf16" modules train in the fp32-equivalent one."""
+        return _lib.PREC_FP32_SIMT if self.precision == "fp32_simt" else _lib.PREC_FP32_3XBF16
+
     def _launch(self, cams, uv, interval, z, b, R, ray_range=None, debug_taps=None, train=False, pw=None):
         """Fill ``car_render_args`` and enqueue ``car_render_forward``.  Returns (out, args, keep)
         where ``keep`` holds every tensor the argument struct points to."""
         lib = _lib.load()
         dev = z[0].device
         H, W, P = self.H, self.W, self.npoints
-        prec = _lib.PREC_FP32_SIMT if train else _lib.PRECISIONS[self.precision]
+        prec = self._train_precision() if train else _lib.PRECISIONS[self.precision]
         feat_bf16 = False if train else (
             (self.feature_dtype == "bf16") if self.feature_dtype else (prec == _lib.PREC_BF16))
         if pw is None:
@@ -452,7 +459,7 @@ class _RenderFunction(torch.autograd.Function):
         want_feat = any(ctx.needs_input_grad[7:10])
         d_feat = [torch.zeros(t.shape[0], t.shape[2], t.shape[3], t.shape[1], device=dev) for t in ctx.z_like] \
             if want_feat else None
-        ws = torch.empty(lib.car_backward_workspace_bytes(a.P, nr), dtype=torch.uint8, device=dev)
+        ws = torch.empty(lib.car_backward_workspace_bytes(a.precision, a.P, nr), dtype=torch.uint8, device=dev)
         bw = _lib.car_backward_args()
         bw.abi_version = _lib.ABI_VERSION
         bw.fwd = C_pointer(a)

@@ -160,9 +160,11 @@ typedef struct car_render_args {
                                      attention tail (encode: P % 64 == 0; tail: P == 64 or 128; else the unfused path).
                                      debug.interp needs bit 0 clear, debug.key/q2 bit 1 clear.   */
   int32_t train;                  /* 1: training-mode forward (reference training.py:92): the whole
-                                     ray range is processed as one chunk on the unfused fp32 path and
+                                     ray range is processed as one chunk on the unfused path and
                                      every activation stays in `workspace` (>= car_train_workspace_bytes)
-                                     for car_render_backward.  Needs CAR_PREC_FP32_SIMT, fp32 maps.  */
+                                     for car_render_backward.  CAR_PREC_FP32_SIMT (exact fp32) or
+                                     CAR_PREC_FP32_3XBF16 (per-sample GEMMs of forward AND backward on
+                                     tcgen05, hi + lo bf16 operands); fp32 maps.               */
   int32_t chunk_rays;             /* rays per workspace chunk; 0 = car_default_chunk_rays().  The library
                                      uses exactly this chunk (clipped to the ray range) and fails with -8
                                      if `workspace_bytes` < car_workspace_bytes(precision, P, chunk, use_fused) */
@@ -208,13 +210,13 @@ typedef struct car_backward_args {
   float *d_feat[3];               /* packed NHWC fp32 (b*2,h_l,w_l,C_l) feature-map gradients,
                                      accumulated into (scatter-add of the bilinear taps =
                                      grid_sample backward); all NULL skips them                  */
-  void *workspace;                /* >= car_backward_workspace_bytes(P, rays)                   */
+  void *workspace;                /* >= car_backward_workspace_bytes(precision, P, rays)        */
   size_t workspace_bytes;
   void *stream;
 } car_backward_args;
 
 size_t car_train_workspace_bytes(int precision, int P, int rays);
-size_t car_backward_workspace_bytes(int P, int rays);
+size_t car_backward_workspace_bytes(int precision, int P, int rays);
 int car_render_backward(const car_backward_args *args);
 /* NHWC fp32 gradient buffer -> the NCHW layout of the encoder output (inverse of car_pack_features). */
 int car_unpack_features(const float *nhwc, float *nchw, int bn, int C, int h, int w, void *stream);

@@ -16,6 +16,13 @@ extern "C" {
 /* Micro-benchmark: cycles for iters*nops back-to-back tcgen05.mma (M x N x 16, bf16) from resident smem. */
 int car_mma_rate_test(int cg, int M, int N, int sw, int iters, int nops, int ctas, void *out_u64, void *stream);
 
+/* A/B of the bilinear tap fetch (csrc/car_tap_fetch_ab.cu): variant 0 = LDG producers with a rolling window (the
+ * fused kernel's scheme), variant 1 = TMA tile::gather4 of the four tap rows into a shared-memory ring of `nslot`
+ * 32 KB stages.  map: [pixels][C] fp32; taps: [n_rows][4] pixel indices; wts: [n_rows][4]; out: [n_rows][C] bf16.
+ * Returns 0 and the milliseconds per launch (average of `iters` launches after one warm-up).                     */
+int car_tap_fetch_ab(const float *map, int pixels, int C, const int *taps, const float *wts, void *out, int n_rows,
+                     int variant, int box_rows, int nslot, int ctas_per_sm, int iters, float *ms, void *stream);
+
 /* CTA-pair (cta_group::2) tcgen05 GEMM, the building block of the fused per-ray kernel, exported
  * for tests: C[M][N] = A·W^T (+bias); N is processed as `nch` MMA chunks; `dump` (optional)
  * receives the raw TMEM image [pairs*2][128 lanes][N/2] of each pair's first tile. */

@@ -31,6 +31,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--no-feature-grads", action="store_true")
     ap.add_argument("--torch-adam", action="store_true", help="A/B: per-parameter all-reduce + clip + torch.optim.Adam")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32_simt"],
+                    help="fp32: per-sample GEMMs of forward and backward on tcgen05 (hi + lo bf16); fp32_simt: exact fp32")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -43,7 +45,7 @@ def main():
     lib = _lib.load()
     inp = synthetic.to_device(synthetic.make_inputs(a.scenes, a.size, a.size, seed=rank, rays=a.rays), dev)
     z = [t.to(dev).requires_grad_(not a.no_feature_grads) for t in synthetic.make_features(a.scenes, a.size, seed=rank)]
-    m = CrossAttentionRenderer(n_view=2, npoints=a.samples).to(dev)
+    m = CrossAttentionRenderer(n_view=2, npoints=a.samples, precision=a.precision).to(dev)
     m.load_state_dict(synthetic.make_state_dict(seed=0), strict=False)
     m.H = m.W = a.size
     m.train()
@@ -55,13 +57,24 @@ def main():
     else:
         opt = FlatAdam(m.parameters(), lr=5e-5, betas=(0.99, 0.999))
 
+    marks = []
+
+    def mark():
+        if marks is not None and len(marks) < 4:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append(e)
+
     def step():
         opt.zero_grad()
         for t in z:
             t.grad = None
+        mark()
         out = m(inp, z=z)
         loss = (out["rgb"] - target).abs().mean()          # image_loss (loss_functions.py:74-80)
+        mark()
         loss.backward()
+        mark()
         if a.torch_adam:
             if world > 1:                                   # training.py:21-28: one all_reduce per parameter
                 for p in m.parameters():
@@ -72,6 +85,7 @@ def main():
             opt.step()
         else:
             opt.step(max_grad_norm=1.0)
+        mark()
         return loss.detach()
 
     def sync():
@@ -82,6 +96,11 @@ def main():
     for _ in range(a.warmup):
         step()
     sync()
+    marks.clear()                  # one step split into forward / backward / all-reduce + optimiser (device time)
+    step()
+    sync()
+    split = {k: round(marks[i].elapsed_time(marks[i + 1]), 3) for i, k in enumerate(("forward_ms", "backward_ms", "allreduce_optim_ms"))}
+    marks = None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
@@ -105,10 +124,10 @@ def main():
         print(json.dumps({"metric": "train_step_rays_per_s (renderer fwd+bwd + optimiser step, encoder excluded)",
                           "value": round(rays / ms * 1e3, 1), "unit": "rays/s", "ms_per_step": round(ms, 3), "n_gpus": world,
                           "config": {"scenes_per_gpu": a.scenes, "rays_per_scene": R, "samples": a.samples, "size": a.size,
-                                     "feature_grads": not a.no_feature_grads,
+                                     "feature_grads": not a.no_feature_grads, "precision": a.precision,
                                      "optimizer": "torch.optim.Adam + per-parameter all_reduce + clip_grad_norm_" if a.torch_adam
                                      else "FlatAdam: one all_reduce + clip scalar + car_adam_step"},
-                          "kernel_ms_by_stage": stages, "loss": float(loss)}), flush=True)
+                          "step_split": split, "forward_kernel_ms_by_stage": stages, "loss": float(loss)}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -98,7 +98,9 @@ def test_sizes_and_argument_errors(lib):
     assert lib.car_render_forward(None) == -1
     # training / backward sizing and argument checks
     assert lib.car_train_workspace_bytes(0, 64, 192) > lib.car_workspace_bytes(0, 64, 192, 0)
-    assert lib.car_backward_workspace_bytes(64, 192) > lib.car_backward_workspace_bytes(64, 1) > 0
+    assert lib.car_backward_workspace_bytes(0, 64, 192) > lib.car_backward_workspace_bytes(0, 64, 1) > 0
+    assert lib.car_backward_workspace_bytes(1, 64, 192) > lib.car_backward_workspace_bytes(0, 64, 192)
+    assert lib.car_train_workspace_bytes(1, 64, 192) > lib.car_train_workspace_bytes(0, 64, 192)
     bw = _lib.car_backward_args()
     assert lib.car_render_backward(None) == -1
     assert lib.car_render_backward(C.byref(bw)) == -1        # no forward arguments

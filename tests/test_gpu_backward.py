@@ -1,7 +1,8 @@
 """GPU tests of the backward pass (car_render_backward through the drop-in module's autograd
 node) against (1) golden gradients from autograd through the unmodified reference and (2) the
-oracle's autograd on seeded inputs.  Tolerance (exact-fp32 products, different summation order):
-relative L2 error of every gradient tensor <= 1e-3 (measured ~1e-6), single entries within
+oracle's autograd on seeded inputs, for both GEMM back ends of the training path: "fp32" (per-sample
+GEMMs of forward and backward on tcgen05, hi + lo bf16 operands) and "fp32_simt" (exact fp32).
+Tolerance (fp32 or fp32-equivalent products, different summation order): relative L2 error of every gradient tensor <= 1e-3 (measured ~1e-6), single entries within
 3e-2 of the tensor's rms; golden sub-samples: max-abs <= 1e-3 of the rms."""
 import pytest
 import torch
@@ -17,8 +18,13 @@ DEV = "cuda:0"
 GRAD_TOL = 1e-3
 
 
-def make_model(sd, P, H):
-    m = CrossAttentionRenderer(n_view=2, npoints=P, precision="fp32").to(DEV)
+@pytest.fixture(params=["fp32", "fp32_simt"])
+def precision(request):
+    return request.param
+
+
+def make_model(sd, P, H, precision="fp32"):
+    m = CrossAttentionRenderer(n_view=2, npoints=P, precision=precision).to(DEV)
     m.load_state_dict(sd, strict=False)
     m.H = m.W = H
     m.train()
@@ -60,9 +66,9 @@ def assert_grad_close(name, got, ref, tol=GRAD_TOL):
 
 
 @pytest.mark.parametrize("case", GRAD_CASES)
-def test_backward_matches_reference_golden(case):
+def test_backward_matches_reference_golden(case, precision):
     d, cfg, inp, z, sd, g_rgb, g_depth = load_grad_case(case)
-    m = make_model(sd, cfg["P"], cfg["H"])
+    m = make_model(sd, cfg["P"], cfg["H"], precision)
     cams = orc.prepare_cameras(inp)
     out, grads, gz = cuda_grads(m, inp, z, cams, cfg["P"], g_rgb, g_depth)
     assert float((out["rgb"].detach().cpu() - torch.from_numpy(d["out_rgb"])).abs().max()) < 5e-5
@@ -80,7 +86,7 @@ def test_backward_matches_reference_golden(case):
 @pytest.mark.parametrize("b,H,Ht,P,mode,peaky,depth", [(2, 64, 16, 64, "default", False, True),
                                                       (1, 32, 12, 32, "mixed", True, False),
                                                       (3, 32, 8, 8, "mixed", False, True)])
-def test_backward_matches_oracle(b, H, Ht, P, mode, peaky, depth):
+def test_backward_matches_oracle(b, H, Ht, P, mode, peaky, depth, precision):
     inp = synthetic.make_inputs(b, H, Ht, seed=21, mode=mode)
     z = synthetic.make_features(b, H, seed=21)
     sd = synthetic.make_state_dict(seed=21, peaky=peaky)
@@ -90,7 +96,7 @@ def test_backward_matches_oracle(b, H, Ht, P, mode, peaky, depth):
     g_depth = torch.randn(b, R, 1, generator=g) * 0.25 if depth else None
     cams = orc.prepare_cameras(inp)
     _, ref, ref_z = orc.render_grad(sd, inp, z, H, H, P, g_rgb, g_depth, cams=cams)
-    m = make_model(sd, P, H)
+    m = make_model(sd, P, H, precision)
     _, grads, gz = cuda_grads(m, inp, z, cams, P, g_rgb, g_depth)
     for name in HOT_PATH_PARAMS:
         assert_grad_close(name, grads[name], ref[name])
@@ -98,7 +104,7 @@ def test_backward_matches_oracle(b, H, Ht, P, mode, peaky, depth):
         assert_grad_close(f"z{i}", gz[i], ref_z[i])
 
 
-def test_backward_depth_only_and_no_feature_grads():
+def test_backward_depth_only_and_no_feature_grads(precision):
     """Only the depth cotangent; feature maps without requires_grad (their scatter is skipped)."""
     b, H, Ht, P = 1, 32, 8, 16
     inp = synthetic.make_inputs(b, H, Ht, seed=3)
@@ -107,7 +113,7 @@ def test_backward_depth_only_and_no_feature_grads():
     g_depth = torch.randn(b, Ht * Ht, 1, generator=torch.Generator().manual_seed(1))
     cams = orc.prepare_cameras(inp)
     _, ref, _ = orc.render_grad(sd, inp, z, H, H, P, None, g_depth, cams=cams)
-    m = make_model(sd, P, H)
+    m = make_model(sd, P, H, precision)
     _, grads, _ = cuda_grads(m, inp, z, cams, P, None, g_depth, need_z=False)
     for name in HOT_PATH_PARAMS:
         assert_grad_close(name, grads[name], ref[name])
@@ -115,7 +121,7 @@ def test_backward_depth_only_and_no_feature_grads():
     assert float(grads["phi.lin_out.weight"].abs().max()) == 0.0
 
 
-def test_backward_ray_shards_sum_to_full():
+def test_backward_ray_shards_sum_to_full(precision):
     """Gradients are additive over ray shards (the multi-GPU split: each rank back-propagates its
     rays, the flat gradient buffer is all-reduced)."""
     b, H, Ht, P = 2, 32, 8, 16
@@ -125,7 +131,7 @@ def test_backward_ray_shards_sum_to_full():
     R = Ht * Ht
     g_rgb = torch.randn(b, 1, R, 3, generator=torch.Generator().manual_seed(2))
     cams = orc.prepare_cameras(inp)
-    m = make_model(sd, P, H)
+    m = make_model(sd, P, H, precision)
     _, full, full_z = cuda_grads(m, inp, z, cams, P, g_rgb, None)
     cut = 37
     _, ga, za = cuda_grads(m, inp, z, cams, P, g_rgb, None, ray_range=(0, cut))
@@ -136,14 +142,14 @@ def test_backward_ray_shards_sum_to_full():
         assert_grad_close(f"z{i}", za[i] + zb[i], full_z[i], 1e-4)
 
 
-def test_training_step_reduces_loss():
+def test_training_step_reduces_loss(precision):
     """A few Adam steps on the renderer weights through the CUDA forward/backward lower an L1
     image loss (the reference's image_loss, loss_functions.py:74-80)."""
     b, H, Ht, P = 1, 32, 8, 16
     inp = synthetic.make_inputs(b, H, Ht, seed=4)
     z = [t.to(DEV) for t in synthetic.make_features(b, H, seed=4)]
     sd = synthetic.make_state_dict(seed=4)
-    m = make_model(sd, P, H)
+    m = make_model(sd, P, H, precision)
     target = torch.rand(b, 1, Ht * Ht, 3, device=DEV) * 2 - 1
     opt = torch.optim.Adam(m.parameters(), lr=5e-4)
     di = synthetic.to_device(inp, DEV)
