@@ -98,7 +98,7 @@ class car_backward_args(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("fwd", C.POINTER(car_render_args)),
                 ("d_rgb", c_fp), ("d_depth_ray", c_fp), ("grads", car_weight_grads),
                 ("d_feat", c_fp * 3), ("workspace", c_fp), ("workspace_bytes", C.c_size_t),
-                ("stream", c_fp)]
+                ("stream", c_fp), ("precision", C.c_int32)]
 
 
 # every symbol include/car_b200.h declares: (restype, argtypes)
@@ -129,7 +129,7 @@ SYMBOLS = {
 TEST_SYMBOLS = {
     "car_mma_rate_test": (C.c_int, [C.c_int] * 7 + [c_fp, c_fp]),
     "car_gemm_pair_test": (C.c_int, [c_fp] * 7 + [C.c_int] * 8 + [c_fp]),
-    "car_tap_fetch_ab": (C.c_int, [c_fp, C.c_int, C.c_int, c_fp, c_fp, c_fp, C.c_int] + [C.c_int] * 5 + [c_fp, c_fp]),
+    "car_tap_fetch_ab": (C.c_int, [c_fp, C.c_int, C.c_int, c_fp, c_fp, c_fp, C.c_int] + [C.c_int] * 5 + [c_fp, c_fp, C.c_int]),
 }
 
 _lib = None

@@ -360,19 +360,20 @@ int car_render_backward(const car_backward_args *pb) {
   const car_render_args &a = *b.fwd;
   if (b.abi_version != CAR_ABI_VERSION || a.abi_version != CAR_ABI_VERSION) { set_error("ABI version mismatch"); return -2; }
   if (!a.train || a.precision == CAR_PREC_BF16) { set_error("car_render_backward needs the arguments of a train=1 forward (CAR_PREC_FP32_SIMT or CAR_PREC_FP32_3XBF16)"); return -12; }
-  const bool tc = a.precision == CAR_PREC_FP32_3XBF16;
+  if (b.precision != CAR_PREC_FP32_SIMT && b.precision != CAR_PREC_FP32_3XBF16) { set_error("car_render_backward: precision %d (0 or 1)", b.precision); return -5; }
+  const bool tc = b.precision == CAR_PREC_FP32_3XBF16;
   if (!b.d_rgb && !b.d_depth_ray) { set_error("car_render_backward: no cotangent given"); return -6; }
   if (!b.workspace) { set_error("car_render_backward: null workspace"); return -6; }
   const int g0 = a.ray_begin, g1 = a.ray_end, nr = g1 - g0;
   if (nr <= 0) return 0;
-  if (carve_bw(nullptr, a.precision, a.P, nr).bytes > b.workspace_bytes) { set_error("backward workspace too small: %zu bytes", b.workspace_bytes); return -8; }
+  if (carve_bw(nullptr, b.precision, a.P, nr).bytes > b.workspace_bytes) { set_error("backward workspace too small: %zu bytes", b.workspace_bytes); return -8; }
   int dev_count = 0;
   if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) { set_error("no CUDA device (there is no CPU fallback)"); return -7; }
   const bool any_feat = b.d_feat[0] || b.d_feat[1] || b.d_feat[2];
   if (any_feat && !(b.d_feat[0] && b.d_feat[1] && b.d_feat[2])) { set_error("d_feat: give all three levels or none"); return -6; }
 
   const Workspace f = carve((char *)a.workspace, a.precision, a.P, nr, 0, 1);     // saved activations
-  const BwWs w = carve_bw((char *)b.workspace, a.precision, a.P, nr);
+  const BwWs w = carve_bw((char *)b.workspace, b.precision, a.P, nr);
   const car_weights &W = a.weights;
   const car_weight_grads &G = b.grads;
   cudaStream_t st = (cudaStream_t)b.stream;

@@ -97,8 +97,8 @@ k_tap_ldg(TapArgs a) {
 }
 
 // ---- variant 1: TMA tile::gather4 into a shared-memory ring, 256 consumer threads + one issuing warp ----
-__global__ void __launch_bounds__(CONSUMERS + 32)
-k_tap_gather4(const __grid_constant__ CUtensorMap tm, TapArgs a, int nslot) {
+__global__ void __launch_bounds__(CONSUMERS + 64)
+k_tap_gather4(const __grid_constant__ CUtensorMap tm, TapArgs a, int nslot, int issue_warps) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)nslot * STAGE_BYTES);
@@ -106,21 +106,24 @@ k_tap_gather4(const __grid_constant__ CUtensorMap tm, TapArgs a, int nslot) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunks = a.C / KS, n_stages = (a.n_rows / ROWS) * chunks;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < nslot; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CONSUMERS / 32); }
+    for (int s = 0; s < nslot; ++s) { mbar_init(&full[s], issue_warps); mbar_init(&empty[s], CONSUMERS / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (warp == CONSUMERS / 32) {
-    // issuing warp: every lane issues the gather4 of two sample rows per stage
+  if (warp >= CONSUMERS / 32) {
+    // issuing warp(s): every lane issues the gather4 of its sample rows (one warp: two rows per lane; two warps: one)
+    const int iw = warp - CONSUMERS / 32, per = ROWS / (32 * issue_warps);
     int slot = 0; uint32_t phase = 0;
     for (int s = blockIdx.x; s < n_stages; s += gridDim.x) {
       const int row0 = (s / chunks) * ROWS, ch0 = (s % chunks) * KS;
-      const int4 t0 = __ldg(a.taps + row0 + lane), t1 = __ldg(a.taps + row0 + lane + 32);
-      if (lane == 0) { mbar_wait(&empty[slot], phase ^ 1); mbar_expect_tx(&full[slot], STAGE_BYTES); }
+      if (lane == 0) { mbar_wait(&empty[slot], phase ^ 1); mbar_expect_tx(&full[slot], STAGE_BYTES / issue_warps); }
       __syncwarp();
       uint8_t *dst = smem + (size_t)slot * STAGE_BYTES;
-      tma_gather4(dst + lane * 512, &tm, &full[slot], ch0, t0.x, t0.y, t0.z, t0.w);
-      tma_gather4(dst + (lane + 32) * 512, &tm, &full[slot], ch0, t1.x, t1.y, t1.z, t1.w);
+      for (int j = 0; j < per; ++j) {
+        const int rr = (iw * per + j) * 32 + lane;
+        const int4 t = __ldg(a.taps + row0 + rr);
+        tma_gather4(dst + rr * 512, &tm, &full[slot], ch0, t.x, t.y, t.z, t.w);
+      }
       if (++slot == nslot) { slot = 0; phase ^= 1; }
     }
   } else {
@@ -156,7 +159,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 
 // Returns 0 and the average milliseconds per launch in *ms; negative / CUDA error code otherwise.
 extern "C" int car_tap_fetch_ab(const float *map, int pixels, int C, const int *taps, const float *wts, void *out, int n_rows,
-                                int variant, int box_rows, int nslot, int ctas_per_sm, int iters, float *ms, void *stream) {
+                                int variant, int box_rows, int nslot, int ctas_per_sm, int iters, float *ms, void *stream,
+                                int issue_warps) {
   if (!map || !taps || !wts || !out || !ms || C % KS || n_rows % ROWS || iters < 1) return -1;
   cudaStream_t st = (cudaStream_t)stream;
   TapArgs a;
@@ -187,13 +191,14 @@ extern "C" int car_tap_fetch_ab(const float *map, int pixels, int C, const int *
                                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return -11;
-    if (nslot < 1 || nslot > 6) return -1;
+    if (nslot < 1 || nslot > 6 || (issue_warps != 1 && issue_warps != 2)) return -1;
     const size_t smem = (size_t)nslot * STAGE_BYTES + 1024 + 256;
     if ((e = cudaFuncSetAttribute(k_tap_gather4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
     const int grid = sms * (ctas_per_sm > 0 ? ctas_per_sm : 1);
-    k_tap_gather4<<<grid, CONSUMERS + 32, smem, st>>>(tm, a, nslot);
+    const int threads = CONSUMERS + 32 * issue_warps;
+    k_tap_gather4<<<grid, threads, smem, st>>>(tm, a, nslot, issue_warps);
     cudaEventRecord(e0, st);
-    for (int i = 0; i < iters; ++i) k_tap_gather4<<<grid, CONSUMERS + 32, smem, st>>>(tm, a, nslot);
+    for (int i = 0; i < iters; ++i) k_tap_gather4<<<grid, threads, smem, st>>>(tm, a, nslot, issue_warps);
     cudaEventRecord(e1, st);
   }
   e = cudaStreamSynchronize(st);

@@ -275,11 +275,14 @@ class CrossAttentionRenderer(nn.Module):
             out["pixel_val"] = out["pixel_val"].cpu()                   # models.py:570
         return out
 
-    def _train_precision(self):
+    def _train_precision(self, backward=False):
         """Arithmetic of the training forward / backward GEMMs: fp32-equivalent on the tensor cores (hi + lo bf16
         operands, three MMAs per product) unless the module was built with precision="fp32_simt" (exact fp32).
-        There is no single-bf16 training mode: "bf16" modules train in the fp32-equivalent one."""
-        return _lib.PREC_FP32_SIMT if self.precision == "fp32_simt" else _lib.PREC_FP32_3XBF16
+        There is no single-bf16 training mode: "bf16" modules train in the fp32-equivalent one.
+        ``self.backward_precision`` ("fp32" / "fp32_simt", default: same as the forward) picks the gradient
+        GEMMs separately (tests: exact forward + tensor-core backward isolates the GEMM error from ReLU flips)."""
+        name = (getattr(self, "backward_precision", None) if backward else None) or self.precision
+        return _lib.PREC_FP32_SIMT if name == "fp32_simt" else _lib.PREC_FP32_3XBF16
 
     def _launch(self, cams, uv, interval, z, b, R, ray_range=None, debug_taps=None, train=False, pw=None):
         """Fill ``car_render_args`` and enqueue ``car_render_forward``.  Returns (out, args, keep)
@@ -440,6 +443,7 @@ class _RenderFunction(torch.autograd.Function):
         z = [z1.detach(), z2.detach(), z3.detach()]
         out, a, keep = model._launch(cams, uv, interval, z, b, R, ray_range, train=True, pw=pw)
         ctx.args, ctx.keep, ctx.pw = a, keep, pw
+        ctx.backward_precision = model._train_precision(backward=True)
         ctx.z_like = z
         ctx.param_shapes = {n: p.shape for n, p in zip(HOT_PATH_PARAMS, params)}
         res = tuple(out[k] for k in _RenderFunction.OUT_KEYS)
@@ -459,7 +463,8 @@ class _RenderFunction(torch.autograd.Function):
         want_feat = any(ctx.needs_input_grad[7:10])
         d_feat = [torch.zeros(t.shape[0], t.shape[2], t.shape[3], t.shape[1], device=dev) for t in ctx.z_like] \
             if want_feat else None
-        ws = torch.empty(lib.car_backward_workspace_bytes(a.precision, a.P, nr), dtype=torch.uint8, device=dev)
+        bprec = ctx.backward_precision
+        ws = torch.empty(lib.car_backward_workspace_bytes(bprec, a.P, nr), dtype=torch.uint8, device=dev)
         bw = _lib.car_backward_args()
         bw.abi_version = _lib.ABI_VERSION
         bw.fwd = C_pointer(a)
@@ -475,6 +480,7 @@ class _RenderFunction(torch.autograd.Function):
                 bw.d_feat[i] = d_feat[i].data_ptr()
         bw.workspace, bw.workspace_bytes = ws.data_ptr(), ws.numel()
         bw.stream = torch.cuda.current_stream(dev).cuda_stream
+        bw.precision = bprec
         with torch.cuda.device(dev):
             _lib.check(lib.car_render_backward(bw), "car_render_backward")
         gsd = grads.unpack(ctx.param_shapes)

@@ -213,6 +213,9 @@ typedef struct car_backward_args {
   void *workspace;                /* >= car_backward_workspace_bytes(precision, P, rays)        */
   size_t workspace_bytes;
   void *stream;
+  int32_t precision;              /* arithmetic of the gradient GEMMs of the per-sample layers:
+                                     CAR_PREC_FP32_SIMT (exact fp32) or CAR_PREC_FP32_3XBF16 (tcgen05,
+                                     hi + lo bf16 operands).  Independent of fwd->precision.    */
 } car_backward_args;
 
 size_t car_train_workspace_bytes(int precision, int P, int rays);

@@ -18,10 +18,11 @@ int car_mma_rate_test(int cg, int M, int N, int sw, int iters, int nops, int cta
 
 /* A/B of the bilinear tap fetch (csrc/car_tap_fetch_ab.cu): variant 0 = LDG producers with a rolling window (the
  * fused kernel's scheme), variant 1 = TMA tile::gather4 of the four tap rows into a shared-memory ring of `nslot`
- * 32 KB stages.  map: [pixels][C] fp32; taps: [n_rows][4] pixel indices; wts: [n_rows][4]; out: [n_rows][C] bf16.
+ * 32 KB stages (tensor-map box = 1 row x 32 columns; a 4-row box is rejected by the hardware).  map: [pixels][C] fp32; taps: [n_rows][4] pixel indices; wts: [n_rows][4]; out: [n_rows][C] bf16.
  * Returns 0 and the milliseconds per launch (average of `iters` launches after one warm-up).                     */
 int car_tap_fetch_ab(const float *map, int pixels, int C, const int *taps, const float *wts, void *out, int n_rows,
-                     int variant, int box_rows, int nslot, int ctas_per_sm, int iters, float *ms, void *stream);
+                     int variant, int box_rows, int nslot, int ctas_per_sm, int iters, float *ms, void *stream,
+                     int issue_warps /* 1 or 2 warps issuing the gather4 instructions */);
 
 /* CTA-pair (cta_group::2) tcgen05 GEMM, the building block of the fused per-ray kernel, exported
  * for tests: C[M][N] = A·W^T (+bias); N is processed as `nch` MMA chunks; `dump` (optional)

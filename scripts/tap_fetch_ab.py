@@ -45,9 +45,9 @@ def run_one(a):
     ms = C.c_float()
     rc = lib.car_tap_fetch_ab(fmap.data_ptr(), h * w, 256, taps.data_ptr(), wts.data_ptr(), out.data_ptr(), n,
                               a.variant, a.box_rows, a.nslot, a.ctas_per_sm, a.iters, C.byref(ms),
-                              torch.cuda.current_stream().cuda_stream)
+                              torch.cuda.current_stream().cuda_stream, a.issue_warps)
     res = {"variant": "ldg" if a.variant == 0 else "tma_gather4", "box_rows": a.box_rows if a.variant else None,
-           "nslot": a.nslot if a.variant else None, "ctas_per_sm": a.ctas_per_sm, "map_mb": h * w * 256 * 4 / 2**20,
+           "nslot": a.nslot if a.variant else None, "issue_warps": a.issue_warps if a.variant else None, "ctas_per_sm": a.ctas_per_sm, "map_mb": h * w * 256 * 4 / 2**20,
            "rows": n, "rc": rc}
     if rc == 0:
         k = 8192
@@ -66,6 +66,7 @@ def main():
     ap.add_argument("--box_rows", type=int, default=1)
     ap.add_argument("--nslot", type=int, default=4)
     ap.add_argument("--ctas_per_sm", type=int, default=0)
+    ap.add_argument("--issue_warps", type=int, default=1)
     ap.add_argument("--rays", type=int, default=16384)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--big", action="store_true")
@@ -73,7 +74,8 @@ def main():
     if a.one:
         return run_one(a)
     cfgs = [dict(variant=0, ctas_per_sm=c) for c in (1, 2, 3, 4)]
-    cfgs += [dict(variant=1, box_rows=br, nslot=ns) for br in (1, 4) for ns in (2, 4, 6)]
+    cfgs += [dict(variant=1, box_rows=1, nslot=ns, issue_warps=iw) for ns in (2, 6) for iw in (1, 2)]
+    cfgs += [dict(variant=1, box_rows=4, nslot=4)]        # rejected by the hardware (gather4 wants a one-row box)
     for big in (False, True):
         for c in cfgs:
             cmd = [sys.executable, os.path.abspath(__file__), "--one", "--rays", str(a.rays), "--iters", str(a.iters)]

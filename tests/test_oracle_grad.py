@@ -28,16 +28,22 @@ def load_grad_case(name):
     return d, cfg, inp, z, sd, g_rgb, g_depth
 
 
-def check_against_golden(d, name, grad, tol):
-    """Compare a gradient tensor with the stored strided sub-sample + norm."""
+def check_against_golden(d, name, grad, tol, entry_tol=None, tail=True):
+    """Compare a gradient tensor with the stored strided sub-sample + norm.  ``entry_tol`` (default: ``tol``)
+    bounds the worst single entry; the norm is held to ``tol`` and so are 99.5 % of the sampled entries
+    (``tail``; without it only the median entry, at 1e-4 of the rms)."""
     ref = torch.from_numpy(d["g:" + name])
     stride = int(d["s:" + name])
     nrm = float(d["n:" + name])
     got = grad.detach().cpu().reshape(-1)[::stride]
     scale = max(nrm / max(grad.numel(), 1) ** 0.5, 1e-12)        # rms of the reference gradient
-    err = float((got - ref).abs().max()) / scale
+    rel = (got - ref).abs() / scale
+    err = float(rel.max())
+    q = float(torch.quantile(rel.double(), 0.995)) if rel.numel() > 1 else err
     nerr = abs(float(grad.double().norm()) - nrm) / max(nrm, 1e-12)
-    assert err < tol and nerr < tol, (name, err, nerr)
+    if not tail:
+        q = float(rel.median()) * (tol / 1e-4)          # median <= 1e-4
+    assert err < (entry_tol or tol) and q < tol and nerr < tol, (name, err, q, nerr, int((rel >= tol).sum()), rel.numel())
 
 
 @pytest.mark.parametrize("case", CASES)
