@@ -15,7 +15,8 @@ K_ENC = 592
 GEOM_STRIDE = 32
 
 STAGES = ("raysetup", "sample_geom", "gather", "gemm_enc1", "gemm_enc2", "gemm_kv", "gemm_small",
-          "attention", "phi", "pack", "fused", "backward")
+          "attention", "phi", "pack", "fused", "backward",
+          "bwd_dgrad", "bwd_wgrad", "bwd_operand_copies", "bwd_scatter")   # backward = attention / colour-MLP / per-ray part
 
 _LIB_PATH = os.environ.get("CAR_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcar_b200.so")
 

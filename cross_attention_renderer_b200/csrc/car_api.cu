@@ -37,8 +37,10 @@ int sm_count() {
 
 // ---- optional per-stage event timing -------------------------------------------------
 struct ProfRec { cudaEvent_t a, b; int stage; };
-static thread_local bool g_prof_on = false;
-static thread_local std::vector<ProfRec> *g_prof = nullptr;
+// process-wide (not thread_local): autograd runs car_render_backward on its own thread and its launches belong to the
+// profile the calling thread opened; profiling is a single-caller diagnostic
+static bool g_prof_on = false;
+static std::vector<ProfRec> *g_prof = nullptr;
 static thread_local int g_stage = CAR_ST_GEMM_SMALL;
 void set_stage(int s) { g_stage = s; }
 int cur_stage() { return g_stage; }

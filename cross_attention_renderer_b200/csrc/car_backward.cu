@@ -327,12 +327,14 @@ GemmEpi accum() { GemmEpi e = plain(); e.accumulate = 1; return e; }
 // data gradient:  dA[M][K] = dY[M][N] · W[N][K]   computed as gemm(dY, W^T) with WT = [K][N]
 void dgrad(const float *dY, int ldy, const float *WT, int N, int K, float *dA, int lda, int M, const GemmEpi &e,
            cudaStream_t st) {
+  StageScope ss(CAR_ST_BWD_DGRAD);
   launch_gemm_simt(dY, ldy, WT, N, dA, lda, M, K, N, e, st);
 }
 
 void wgrad(const float *dY, int ldy, const float *A, int lda, const car_mat_grad &g, int ldw, int M, int N, int K,
            int relu_a, cudaStream_t st) {
   if (!g.w) return;
+  StageScope ss(CAR_ST_BWD_WGRAD);
   launch_wgrad_simt(dY, ldy, A, lda, g.w, ldw, g.bias, M, N, K, relu_a, st);
 }
 
@@ -411,12 +413,17 @@ int car_render_backward(const car_backward_args *pb) {
   // (+ its bias gradient); act(): transposed copy of the saved activation; wg(): dW += dY^T·A; dg(): dA = dY·W.
   int rc = 0;
   auto ops = [&](const float *dY, int ld, int M, int N, bool rowmajor, const car_mat_grad &g) {
+    StageScope ss(CAR_ST_BWD_OPS);
     launch_split_ops(dY, ld, M, N, rowmajor ? w.dy_hi : nullptr, rowmajor ? w.dy_lo : nullptr, g.w ? w.dyT_hi : nullptr,
                      g.w ? w.dyT_lo : nullptr, g.w ? g.bias : nullptr, st);
   };
-  auto act = [&](const float *A, int ld, int M, int K) { launch_split_ops(A, ld, M, K, nullptr, nullptr, w.aT_hi, w.aT_lo, nullptr, st); };
+  auto act = [&](const float *A, int ld, int M, int K) {
+    StageScope ss(CAR_ST_BWD_OPS);
+    launch_split_ops(A, ld, M, K, nullptr, nullptr, w.aT_hi, w.aT_lo, nullptr, st);
+  };
   auto wg = [&](const uint16_t *aT_hi, const uint16_t *aT_lo, const car_mat_grad &g, int ldw, int M, int N, int K) {
     if (!g.w || rc) return;
+    StageScope ss(CAR_ST_BWD_WGRAD);
     for (int k0 = 0; k0 < K && !rc; k0 += CAR_C_FEAT) {      // K = 592: the 576 feature columns, then the 16 others
       const int kn = K - k0 < CAR_C_FEAT ? K - k0 : CAR_C_FEAT;
       UmmaOut o; o.f32 = g.w + k0; o.hi = nullptr; o.lo = nullptr; o.ldc = ldw; o.atomic = 1;
@@ -425,6 +432,7 @@ int car_render_backward(const car_backward_args *pb) {
   };
   auto dg = [&](const uint16_t *wT_hi, const uint16_t *wT_lo, int N, int K, float *dA, int lda, int M, const GemmEpi &e) {
     if (rc) return;
+    StageScope ss(CAR_ST_BWD_DGRAD);
     UmmaOut o; o.f32 = dA; o.f32_add = e.accumulate ? dA : nullptr; o.hi = nullptr; o.lo = nullptr; o.ldc = lda;
     rc = launch_gemm_umma(w.dy_hi, w.dy_lo, N, wT_hi, wT_lo, N, M, K, N, 1, e, o, st);
   };
@@ -445,7 +453,9 @@ int car_render_backward(const car_backward_args *pb) {
     }
     cudaMemcpyAsync(w.x3, w.xrun, (size_t)nr * 128 * 4, cudaMemcpyDeviceToDevice, st);
   }
+  prof_pre(-1, st);
   k_rgb_bwd<<<nr, 128, 0, st>>>(a, g0, nr, b.d_rgb, f.overlap, W.phi_out.f32, w.x3, w.d_rgb3, w.dx);
+  prof_post(st);
   count_launch();
   wgrad(w.d_rgb3, 4, w.x3, 128, G.phi_out, 128, nr, 3, 128, 1, st);
   for (int i = 2; i >= 0; --i) {
@@ -460,7 +470,9 @@ int car_render_backward(const car_backward_args *pb) {
   wgrad(w.dx, 128, f.c18, 32, G.phi_in, 32, nr, 128, 32, 0, st);
 
   // ---- attention round 2 and the repeat-query MLP (models.py:548-565) ----
+  prof_pre(-1, st);
   k_attn2_bwd<<<nr, BT, 0, st>>>(P, w.d_zfin, f.value, f.att2, f.q1, f.q2, w.ds, w.dq1, w.dv, w.d_zsum);
+  prof_post(st);
   count_launch();
   if (tc) {
     ops(w.ds, 128, rows, 128, true, G.rep2);
@@ -476,7 +488,9 @@ int car_render_backward(const car_backward_args *pb) {
     dgrad(w.ds, 128, w.rep2T, 128, 128, w.dhid, 128, rows, masked(f.hid_r, 128), st);
     wgrad(w.dhid, 128, f.geom + G_LOCAL, CAR_GEOM_STRIDE, G.rep1_loc, 16, rows, 128, 16, 0, st);
   }
+  prof_pre(-1, st);
   k_raysum128<<<nr, 128, 0, st>>>(w.dhid, 2 * P, w.drowbias);
+  prof_post(st);
   count_launch();
   wgrad(w.drowbias, 128, f.g, 128, G.rep1_g, 128, nr, 128, 128, 0, st);
   dgrad(w.drowbias, 128, w.rep1gT, 128, 128, w.dg, 128, nr, plain(), st);
@@ -484,7 +498,9 @@ int car_render_backward(const car_backward_args *pb) {
   dgrad(w.dg, 128, w.enclatT, 128, L, w.d_zsum, L, nr, accum(), st);
 
   // ---- attention round 1 + depth (models.py:532-545,577-594) ----
+  prof_pre(-1, st);
   k_attn1_bwd<<<nr, BT, 0, st>>>(a, g0, w.d_zsum, b.d_depth_ray, f.value, f.key, f.q1, f.geom, w.ds, w.dq1, w.dv);
+  prof_post(st);
   count_launch();
   if (tc) {
     // geometric query (:529)
@@ -516,7 +532,7 @@ int car_render_backward(const car_backward_args *pb) {
     wg(w.aT_hi, w.aT_lo, G.enc1, CAR_K_ENC, rows2, F, CAR_K_ENC);
     if (any_feat) {
       dg(w.enc1T_hi, w.enc1T_lo, F, F, w.dxin, F, rows2, plain());
-      if (!rc) launch_gather_backward(a, g0, g1, f.geom, w.dxin, b.d_feat, st);
+      if (!rc) { StageScope ss(CAR_ST_BWD_SCATTER); launch_gather_backward(a, g0, g1, f.geom, w.dxin, b.d_feat, st); }
     }
     if (rc) return rc;
   } else {
@@ -538,7 +554,7 @@ int car_render_backward(const car_backward_args *pb) {
     wgrad(w.dh1, F, f.x, CAR_K_ENC, G.enc1, CAR_K_ENC, rows2, F, CAR_K_ENC, 0, st);
     if (any_feat) {
       dgrad(w.dh1, F, w.enc1T, F, F, w.dxin, F, rows2, plain(), st);
-      launch_gather_backward(a, g0, g1, f.geom, w.dxin, b.d_feat, st);
+      { StageScope ss(CAR_ST_BWD_SCATTER); launch_gather_backward(a, g0, g1, f.geom, w.dxin, b.d_feat, st); }
     }
   }
   cudaError_t e = cudaGetLastError();

@@ -360,7 +360,7 @@ void launch_gather_backward(const car_render_args &a, int g0, int g1, const floa
   long nrows = (long)(g1 - g0) * 2 * a.P;
   if (nrows <= 0) return;
   unsigned blocks = (unsigned)((nrows * 32 + 255) / 256);
-  prof_pre(CAR_ST_GATHER, st);
+  prof_pre(-1, st);                                   // tagged by the caller (CAR_ST_BWD_SCATTER)
   k_gather_backward<<<blocks, 256, 0, st>>>(a, g0, g1, geom, dx, d_feat[0], d_feat[1], d_feat[2]);
   prof_post(st);
   count_launch();

@@ -301,7 +301,8 @@ int car_last_launch_count(void);
  * ms[0..n) / launches[0..n) (HOST pointers) and stops recording. */
 enum car_stage { CAR_ST_RAYSETUP = 0, CAR_ST_SAMPLE_GEOM, CAR_ST_GATHER, CAR_ST_GEMM_ENC1,
                  CAR_ST_GEMM_ENC2, CAR_ST_GEMM_KV, CAR_ST_GEMM_SMALL, CAR_ST_ATTENTION,
-                 CAR_ST_PHI, CAR_ST_PACK, CAR_ST_FUSED, CAR_ST_BACKWARD, CAR_ST_COUNT };  /* FUSED = gather+enc1+enc2+kv in one kernel */
+                 CAR_ST_PHI, CAR_ST_PACK, CAR_ST_FUSED, CAR_ST_BACKWARD,
+                 CAR_ST_BWD_DGRAD, CAR_ST_BWD_WGRAD, CAR_ST_BWD_OPS, CAR_ST_BWD_SCATTER, CAR_ST_COUNT };  /* FUSED = gather+enc1+enc2+kv in one kernel */
 int car_profile_begin(void);
 int car_profile_end(float *ms, int *launches, int n);
 

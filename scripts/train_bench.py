@@ -127,7 +127,7 @@ def main():
                                      "feature_grads": not a.no_feature_grads, "precision": a.precision,
                                      "optimizer": "torch.optim.Adam + per-parameter all_reduce + clip_grad_norm_" if a.torch_adam
                                      else "FlatAdam: one all_reduce + clip scalar + car_adam_step"},
-                          "step_split": split, "forward_kernel_ms_by_stage": stages, "loss": float(loss)}), flush=True)
+                          "step_split": split, "kernel_ms_by_stage": stages, "loss": float(loss)}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

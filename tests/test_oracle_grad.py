@@ -31,7 +31,7 @@ def load_grad_case(name):
 def check_against_golden(d, name, grad, tol, entry_tol=None, tail=True):
     """Compare a gradient tensor with the stored strided sub-sample + norm.  ``entry_tol`` (default: ``tol``)
     bounds the worst single entry; the norm is held to ``tol`` and so are 99.5 % of the sampled entries
-    (``tail``; without it only the median entry, at 1e-4 of the rms)."""
+    (``tail``; without it only the median entry, at 5e-3 of the rms)."""
     ref = torch.from_numpy(d["g:" + name])
     stride = int(d["s:" + name])
     nrm = float(d["n:" + name])
@@ -42,7 +42,7 @@ def check_against_golden(d, name, grad, tol, entry_tol=None, tail=True):
     q = float(torch.quantile(rel.double(), 0.995)) if rel.numel() > 1 else err
     nerr = abs(float(grad.double().norm()) - nrm) / max(nrm, 1e-12)
     if not tail:
-        q = float(rel.median()) * (tol / 1e-4)          # median <= 1e-4
+        q = float(rel.median()) * (tol / 5e-3)          # median <= 5e-3 of the rms
     assert err < (entry_tol or tol) and q < tol and nerr < tol, (name, err, q, nerr, int((rel >= tol).sum()), rel.numel())
 
 
