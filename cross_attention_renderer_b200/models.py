@@ -439,7 +439,7 @@ class _RenderFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, cams, uv, interval, b, R, ray_range, z1, z2, z3, *params):
         sd = {n: p.detach() for n, p in zip(HOT_PATH_PARAMS, params)}
-        pw = packing.PackedWeights(sd)
+        pw = packing.PackedWeights(sd, folds=False)
         z = [z1.detach(), z2.detach(), z3.detach()]
         out, a, keep = model._launch(cams, uv, interval, z, b, R, ray_range, train=True, pw=pw)
         ctx.args, ctx.keep, ctx.pw = a, keep, pw

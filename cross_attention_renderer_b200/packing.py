@@ -50,10 +50,30 @@ class PackedMat:
         return m
 
 
-class PackedWeights:
-    """Holds the packed device tensors alive and exposes the ctypes struct."""
+_FOLD64_PERM = None
 
-    def __init__(self, sd):
+
+def _fold64_perm():
+    """K-column order of ``kv_fold64``: the fused kernel's 64-wide H stages (include/car_b200.h)."""
+    global _FOLD64_PERM
+    if _FOLD64_PERM is None:
+        perm = torch.empty(1152, dtype=torch.long)
+        for v in range(2):
+            for q in range(9):
+                c, j = divmod(q, 3)
+                for h in range(2):
+                    dst = v * 576 + q * 64 + h * 32
+                    src = v * 576 + c * 192 + h * 96 + j * 32
+                    perm[dst:dst + 32] = torch.arange(src, src + 32)
+        _FOLD64_PERM = perm
+    return _FOLD64_PERM
+
+
+class PackedWeights:
+    """Holds the packed device tensors alive and exposes the ctypes struct.  ``folds=False`` (training: the unfused
+    kernels read the plain layers only) skips the composed matrices of the fused inference kernels."""
+
+    def __init__(self, sd, folds=True):
         g = lambda n: sd[n]
         P = PackedMat
         self.m = {}
@@ -76,6 +96,8 @@ class PackedWeights:
             self.m[f"phi_fc0{i}"] = P(g(f"phi.blocks.{i}.fc_0.weight"), g(f"phi.blocks.{i}.fc_0.bias"))
             self.m[f"phi_fc1{i}"] = P(g(f"phi.blocks.{i}.fc_1.weight"), g(f"phi.blocks.{i}.fc_1.bias"))
         self.m["phi_out"] = P(g("phi.lin_out.weight"), g("phi.lin_out.bias"))
+        if not folds:
+            return
         # fold query_encode_latent_2 into [latent_value ; key_map] (float64 product, rounded once)
         w2 = g("query_encode_latent_2.weight").reshape(288, 576).double()
         b2 = g("query_encode_latent_2.bias").double()
@@ -86,15 +108,7 @@ class PackedWeights:
         self.m["kv_fold"] = P(fold.float(), bfold.float())
         # the same matrix with its K columns in the order of the fused kernel's 64-wide H stages
         # (include/car_b200.h, car_weights::kv_fold64)
-        perm = torch.empty(1152, dtype=torch.long)
-        for v in range(2):
-            for q in range(9):
-                c, j = divmod(q, 3)
-                for h in range(2):
-                    dst = v * 576 + q * 64 + h * 32
-                    src = v * 576 + c * 192 + h * 96 + j * 32
-                    perm[dst:dst + 32] = torch.arange(src, src + 32)
-        self.m["kv_fold64"] = P(fold.float()[:, perm.to(fold.device)], bfold.float())
+        self.m["kv_fold64"] = P(fold.float()[:, _fold64_perm().to(fold.device)], bfold.float())
         # colour MLP: all ten matrices along K in 64-column blocks (include/car_b200.h, car_weights::phi_pack)
         pad = lambda w_, k_: torch.nn.functional.pad(w_, (0, k_ - w_.shape[1]))
         parts = [pad(self.m["phi_in"].f32, 64)]
@@ -111,7 +125,8 @@ class PackedWeights:
         w = _lib.car_weights()
         for name in ("enc1", "enc2", "value", "key1", "key2", "qry1", "qry2", "rep1_loc",
                      "rep1_g", "rep2", "enc_lat", "phi_in", "phi_out", "kv_fold", "kv_fold64", "rowb_fold", "phi_pack"):
-            setattr(w, name, self.m[name].c_struct())
+            if name in self.m:                       # folds=False leaves the composed matrices null
+                setattr(w, name, self.m[name].c_struct())
         for i in range(3):
             w.phi_z[i] = self.m[f"phi_z{i}"].c_struct()
             w.phi_fc0[i] = self.m[f"phi_fc0{i}"].c_struct()
