@@ -87,7 +87,8 @@ def test_backward_matches_reference_golden(case, precision):
     m = make_model(sd, cfg["P"], cfg["H"], precision)
     cams = orc.prepare_cameras(inp)
     out, grads, gz = cuda_grads(m, inp, z, cams, cfg["P"], g_rgb, g_depth)
-    assert float((out["rgb"].detach().cpu() - torch.from_numpy(d["out_rgb"])).abs().max()) < 5e-5
+    ref_rgb = torch.from_numpy(d["out_rgb"])                      # forward parity: rgb <= 1e-4 relative (hi + lo GEMMs)
+    assert float((out["rgb"].detach().cpu() - ref_rgb).abs().max()) < (5e-5 if precision == "fp32_simt" else 1e-4 * float(ref_rgb.abs().max()))
     for name in HOT_PATH_PARAMS:
         check_against_golden(d, name, grads[name], L2_TOL[precision], ENTRY_TOL[precision], precision != "fp32")
     for i in range(3):
