@@ -75,6 +75,27 @@ def test_packing_algebra():
     assert torch.allclose(torch.cat([zz, zz], -1) @ wz.T, zz @ pw.m["phi_z1"].f32.T, atol=1e-5)
 
 
+def test_training_pack_skips_the_inference_folds_and_precision_selection():
+    """The training path packs the plain layers only (the composed matrices feed the fused inference kernels),
+    and picks its GEMM arithmetic from the module's precision (backward separately on request)."""
+    from cross_attention_renderer_b200 import _lib
+    from cross_attention_renderer_b200.packing import PackedGrads, PackedWeights
+    sd = synthetic.make_state_dict(5)
+    full, plain = PackedWeights(sd), PackedWeights(sd, folds=False)
+    assert set(full.m) - set(plain.m) == {"kv_fold", "kv_fold64", "rowb_fold", "phi_pack"}
+    for k in plain.m:
+        assert torch.equal(plain.m[k].f32, full.m[k].f32)
+    w = plain.c_struct()
+    assert not w.kv_fold.hi and not w.phi_pack.hi and w.enc1.hi and (w.enc1.N, w.enc1.K) == (576, 592)
+    assert set(PackedGrads(plain).g) == set(PackedGrads(full).g)              # gradients exist for the plain layers only
+    m = CrossAttentionRenderer(n_view=2, npoints=8, precision="fp32")
+    assert m._train_precision() == _lib.PREC_FP32_3XBF16 == m._train_precision(backward=True)
+    m.backward_precision = "fp32_simt"
+    assert m._train_precision() == _lib.PREC_FP32_3XBF16 and m._train_precision(backward=True) == _lib.PREC_FP32_SIMT
+    assert CrossAttentionRenderer(n_view=2, npoints=8, precision="fp32_simt")._train_precision() == _lib.PREC_FP32_SIMT
+    assert CrossAttentionRenderer(n_view=2, npoints=8, precision="bf16")._train_precision() == _lib.PREC_FP32_3XBF16
+
+
 def test_synthetic_inputs_are_deterministic():
     a = synthetic.make_inputs(2, 32, 8, seed=3, mode="mixed")
     b = synthetic.make_inputs(2, 32, 8, seed=3, mode="mixed")
