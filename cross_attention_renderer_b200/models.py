@@ -80,7 +80,14 @@ class CrossAttentionRenderer(nn.Module):
         # exact-fp32 kernels behind car_render_forward_general
         self.general = n_view != 2 or no_sample or no_latent_concat
         # image encoder: outside the hot path; plug in any module with the reference's
-        # encoder.forward(rgb, cam2world_encode, n_view) -> [path_2, path_1] contract
+        # encoder.forward(rgb, cam2world_encode, n_view) -> [path_2, path_1] contract, or encoder="dpt_hybrid" for
+        # the reference's own multi-view DPT-hybrid (encoder.py: 123.6 M parameters, the reference's state_dict keys).
+        # The default stays None: forward(input, z=...) - the hot path - does not need one.
+        if isinstance(encoder, str):
+            if encoder != "dpt_hybrid":
+                raise ValueError(f"unknown encoder {encoder!r} (a module, None or 'dpt_hybrid')")
+            from .encoder import DPTHybridEncoder
+            encoder = DPTHybridEncoder(channels_last=True)
         self.encoder = encoder
         hidden = 128
         latent = 512 + 64
@@ -145,8 +152,13 @@ class CrossAttentionRenderer(nn.Module):
             raise RuntimeError(
                 "get_z needs an image encoder (out of the hot path, SURVEY.md §8f): pass "
                 "encoder=<module> to the constructor or call forward(input, z=[z1,z2,z3])")
+        if getattr(self.encoder, "channels_last", False):
+            # NHWC end to end: the packed layout of the renderer is then the encoder's own output (packing.nhwc_view)
+            rgb = rgb.contiguous(memory_format=torch.channels_last)
         z = list(self.encoder.forward(rgb, enc, self.n_view))
         z_conv = self.conv_map(rgb)
+        if getattr(self.encoder, "channels_last", False):
+            z_conv = z_conv.contiguous(memory_format=torch.channels_last)
         if self.no_high_freq:
             z_conv = torch.zeros_like(z_conv)
         return z + [z_conv]

@@ -261,14 +261,30 @@ def unpack_feature_grads(packed, like):
     return out
 
 
+def nhwc_view(t):
+    """The NHWC buffer of a map that already lies in channels_last memory order (what
+    ``encoder.DPTHybridEncoder(channels_last=True)`` and cuDNN's channels_last convolutions produce), as a
+    contiguous (bn, h, w, C) view - or None when the map is NCHW and has to go through ``car_pack_features``."""
+    if t.dim() == 4 and t.shape[1] > 1 and not t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last):
+        v = t.permute(0, 2, 3, 1)
+        assert v.is_contiguous()
+        return v
+    return None
+
+
 def pack_features(z, bf16=False):
     """[z1,z2,z3] NCHW fp32 (device) -> list of packed NHWC buffers via
-    car_pack_features.  One-off per scene batch."""
+    car_pack_features.  One-off per scene batch.  Maps that are already channels_last are taken over as they are
+    (fp32: zero-copy view; bf16: one conversion pass)."""
     lib = _lib.load()
     out = []
     stream = torch.cuda.current_stream().cuda_stream
     for t in z:
         assert t.is_cuda and t.dtype == torch.float32, "features must be fp32 CUDA tensors"
+        v = nhwc_view(t)
+        if v is not None:
+            out.append(v.to(torch.bfloat16) if bf16 else v)
+            continue
         t = t.contiguous()
         bn, Cc, h, w = t.shape
         o = torch.empty(bn, h, w, Cc, dtype=torch.bfloat16 if bf16 else torch.float32, device=t.device)

@@ -6,9 +6,9 @@ files, ``strict=False``; train_realestate10k.py:90-106, training.py:118-120), on
 (train_realestate10k.py:60-73,132-133), PSNR (eval_realestate10k.py:74-75,181-187) — restated on
 argparse + torch only.  The RealEstate10k loaders (``dataset/realestate10k_dataio.py``) are used
 when that package and its data are importable; otherwise ``--synthetic`` scenes (random smooth
-images, wide-baseline cameras) stand in, and the image encoder is the declared stand-in of
-``cross_attention_renderer_b200/standin_encoder.py`` unless ``--encoder_module`` names the
-reference's.
+images, wide-baseline cameras) stand in.  The image encoder is the reference's multi-view DPT-hybrid
+(``cross_attention_renderer_b200/encoder.py``, ``--encoder dpt_hybrid``, the default) or the small declared
+stand-in of ``standin_encoder.py`` (``--encoder standin``) for smoke runs.
 """
 import argparse
 import importlib
@@ -65,8 +65,11 @@ def base_parser(description, train=False):
     p.add_argument("--sidelength", type=int, default=256)
     p.add_argument("--npoints", type=int, default=64)
     p.add_argument("--precision", type=str, default="fp32", choices=["fp32", "bf16", "fp32_simt"])
+    p.add_argument("--encoder", type=str, default="dpt_hybrid", choices=["dpt_hybrid", "standin"],
+                   help="dpt_hybrid: the reference's multi-view DPT-hybrid encoder (encoder.py, the reference's "
+                        "state_dict keys); standin: a small convolutional stand-in for smoke runs")
     p.add_argument("--encoder_module", type=str, default=None,
-                   help="'pkg.mod:factory' returning the reference encoder module; default: stand-in encoder")
+                   help="'pkg.mod:factory' returning an encoder module (overrides --encoder)")
     p.add_argument("--allow_encoder_mismatch", action="store_true", default=False,
                    help="load a checkpoint whose encoder.* tensors do not match this model's encoder (renderer weights only)")
     p.add_argument("--max_steps", type=int, default=None, help="stop after this many iterations / scenes")
@@ -78,8 +81,10 @@ def build_model(opt, device):
     if opt.encoder_module:
         mod, fn = opt.encoder_module.split(":")
         encoder = getattr(importlib.import_module(mod), fn)()
-    else:
+    elif opt.encoder == "standin":
         encoder = StandInEncoder()
+    else:
+        encoder = "dpt_hybrid"
     model = CrossAttentionRenderer(no_multiview=opt.no_multiview, no_sample=opt.no_sample,
                                    no_latent_concat=opt.no_latent_concat, no_high_freq=opt.no_high_freq,
                                    model=opt.model, n_view=opt.views, npoints=opt.npoints,
@@ -105,8 +110,9 @@ def load_checkpoint(model, path, optimizer=None, allow_encoder_mismatch=False):
         raise RuntimeError(
             f"{len(enc_unexpected)} encoder.* tensors of the checkpoint do not fit this model's encoder and "
             f"{len(enc_missing)} encoder parameters stay at their initial values: the renderer would run on "
-            "features the checkpoint was not trained with.  Pass --encoder_module <pkg.mod:factory> for the "
-            "encoder the checkpoint was trained with, or --allow_encoder_mismatch to load the renderer weights only.")
+            "features the checkpoint was not trained with.  Use the encoder the checkpoint was trained with (--encoder "
+            "dpt_hybrid for the reference's, or --encoder_module <pkg.mod:factory>), or --allow_encoder_mismatch to load "
+            "the renderer weights only.")
     return missing, unexpected
 
 

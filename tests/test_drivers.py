@@ -29,20 +29,21 @@ def test_reference_flag_surface():
 
 
 def test_branch_flags_reach_the_model():
-    opt = C.base_parser("t").parse_args(["--experiment_name", "e", "--views", "3"])
+    opt = C.base_parser("t").parse_args(["--experiment_name", "e", "--views", "3", "--encoder", "standin"])
     m = C.build_model(opt, "cpu")
     assert m.n_view == 3 and m.general
-    opt = C.base_parser("t").parse_args(["--experiment_name", "e", "--no_sample"])
+    opt = C.base_parser("t").parse_args(["--experiment_name", "e", "--no_sample", "--encoder", "standin"])
     m = C.build_model(opt, "cpu")
     assert m.no_sample and m.general
-    opt = C.base_parser("t").parse_args(["--experiment_name", "e", "--views", "4"])
+    opt = C.base_parser("t").parse_args(["--experiment_name", "e", "--views", "4", "--encoder", "standin"])
     with pytest.raises(NotImplementedError):
         C.build_model(opt, "cpu")
 
 
 def test_checkpoint_format_roundtrip(tmp_path):
     """Reference file format {'model','optimizer'} with the reference's parameter names, strict=False load."""
-    opt = C.base_parser("t").parse_args(["--experiment_name", "e"])
+    assert C.base_parser("t").parse_args(["--experiment_name", "e"]).encoder == "dpt_hybrid"      # the reference's encoder
+    opt = C.base_parser("t").parse_args(["--experiment_name", "e", "--encoder", "standin"])
     m = C.build_model(opt, "cpu")
     optim = torch.optim.Adam(m.parameters(), lr=1e-4, betas=(0.99, 0.999))
     path = str(tmp_path / "checkpoints" / "model_current.pth")
@@ -62,6 +63,14 @@ def test_checkpoint_format_roundtrip(tmp_path):
     missing, unexpected = C.load_checkpoint(m2, path, allow_encoder_mismatch=True)
     assert "encoder.pretrained.model.cls_token" in unexpected
     assert torch.equal(m2.phi.lin_out.weight, m.phi.lin_out.weight)
+    # the DPT-hybrid encoder carries the reference's encoder.* keys: such a checkpoint loads without any override
+    opt3 = C.base_parser("t").parse_args(["--experiment_name", "e", "--encoder", "dpt_hybrid"])
+    m3 = C.build_model(opt3, "cpu")
+    assert m3.state_dict()["encoder.pretrained.model.cls_token"].shape == (1, 1, 768)
+    path3 = str(tmp_path / "checkpoints" / "dpt.pth")
+    torch.save({"model": m3.state_dict(), "optimizer": {}}, path3)
+    missing, unexpected = C.load_checkpoint(C.build_model(opt3, "cpu"), path3)
+    assert not list(missing) and not list(unexpected)
 
 
 def test_synthetic_batch_layout_and_psnr():
@@ -77,11 +86,13 @@ def test_synthetic_batch_layout_and_psnr():
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not HAS_GPU, reason="needs a CUDA device")
-def test_train_eval_render_end_to_end(tmp_path):
+@pytest.mark.parametrize("encoder", ["standin", "dpt_hybrid"])
+def test_train_eval_render_end_to_end(tmp_path, encoder):
     import train_realestate10k as T
     import eval_realestate10k as E
     import render_realestate10k_traj as R
-    common = ["--experiment_name", "t", "--logging_root", str(tmp_path), "--sidelength", "64", "--synthetic", "4"]
+    common = ["--experiment_name", "t", "--logging_root", str(tmp_path), "--sidelength", "64", "--synthetic", "4",
+              "--encoder", encoder]
     T.main(common + ["--batch_size", "2", "--max_steps", "3", "--steps_til_summary", "1", "--lr", "1e-4"])
     ck = os.path.join(str(tmp_path), "t", "checkpoints", "model_final.pth")
     assert os.path.exists(ck) and os.path.exists(os.path.join(os.path.dirname(ck), "model_current.pth"))
@@ -91,5 +102,6 @@ def test_train_eval_render_end_to_end(tmp_path):
     opt = C.base_parser("t").parse_args(["--experiment_name", "e"])
     torch.manual_seed(0)
     E.main(common + ["--checkpoint_path", ck, "--max_steps", "2"])
-    R.main(common[:4] + ["--sidelength", "64", "--synthetic", "1", "--frames", "2", "--checkpoint_path", ck])
+    R.main(common[:4] + ["--sidelength", "64", "--synthetic", "1", "--frames", "2", "--checkpoint_path", ck,
+                         "--encoder", encoder])
     assert os.path.exists(os.path.join(str(tmp_path), "vis", "scene_0000"))
