@@ -158,3 +158,26 @@ def test_get_z_through_the_module_and_nhwc_takeover():
         assert float(m.get_z(inp)[2].abs().max()) == 0.0       # models.py:183-184
     with pytest.raises(ValueError):
         CrossAttentionRenderer(n_view=2, encoder="resnet")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_channels_last_maps_render_identically(precision):
+    """Maps handed over in NHWC memory order (the encoder's output) are taken as the packed layout without the
+    car_pack_features pass: same bits as rendering from the NCHW copies (bf16: the same round-to-nearest conversion)."""
+    dev = "cuda:0"
+    b, H, Ht, P = 1, 64, 16, 64
+    inp = synthetic.to_device(synthetic.make_inputs(b, H, Ht, seed=41), dev)
+    z = [t.to(dev) for t in synthetic.make_features(b, H, seed=41)]
+    zc = [t.contiguous(memory_format=torch.channels_last) for t in z]
+    assert all(packing.nhwc_view(t) is not None for t in zc) and all(packing.nhwc_view(t) is None for t in z)
+    m = CrossAttentionRenderer(n_view=2, npoints=P, precision=precision).to(dev).eval()
+    m.load_state_dict(synthetic.make_state_dict(seed=41), strict=False)
+    m.H = m.W = H
+    with torch.no_grad():
+        a = m(inp, z=z)
+        m.release_features()
+        c = m(inp, z=zc)
+    for k in ("rgb", "depth_ray", "at_wt", "valid_mask"):
+        assert torch.equal(a[k], c[k]), k
