@@ -10,8 +10,9 @@ scenes: 256x256 target rays, 2 source views, 64 epipolar samples, 12 scenes per 
 config 2; at N>1 every rank renders its own 12 scenes = config 3's layout, weak scaling, tiles
 all-gathered at the end of the step).  Prints ONE JSON line.  After the headline region the same
 line gets `extra_configs` (config 3's bf16 arithmetic at this N; config 4 at N=1), each measured the
-same way with its own roofline and parity, and `reference_gpu`: the UNMODIFIED reference (oracle/_ref)
-timed on the same B200 (N=1 only).
+same way with its own roofline and parity; `general_branches` (N=1: the reference's other forward branches,
+n_view 1 / 3 and no_latent_concat, one scene each, with a parity check); at N>1 a strong-scaling block; and
+`reference_gpu`: the UNMODIFIED reference (oracle/_ref) timed on the same B200 (N=1 only).
 """
 import argparse
 import json
