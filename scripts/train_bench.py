@@ -31,6 +31,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--no-feature-grads", action="store_true")
     ap.add_argument("--torch-adam", action="store_true", help="A/B: per-parameter all-reduce + clip + torch.optim.Adam")
+    ap.add_argument("--with-encoder", action="store_true",
+                    help="C5 as the reference trains it: get_z (multi-view DPT-hybrid, encoder.py) inside the step, its "
+                         "parameters in the optimiser")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32_simt"],
                     help="fp32: per-sample GEMMs of forward and backward on tcgen05 (hi + lo bf16); fp32_simt: exact fp32")
     a = ap.parse_args()
@@ -45,7 +48,10 @@ def main():
     lib = _lib.load()
     inp = synthetic.to_device(synthetic.make_inputs(a.scenes, a.size, a.size, seed=rank, rays=a.rays), dev)
     z = [t.to(dev).requires_grad_(not a.no_feature_grads) for t in synthetic.make_features(a.scenes, a.size, seed=rank)]
-    m = CrossAttentionRenderer(n_view=2, npoints=a.samples, precision=a.precision).to(dev)
+    m = CrossAttentionRenderer(n_view=2, npoints=a.samples, precision=a.precision,
+                               encoder="dpt_hybrid" if a.with_encoder else None).to(dev)
+    if a.with_encoder:
+        inp["context"]["rgb"] = torch.rand(a.scenes, 2, a.size, a.size, 3, device=dev) * 2 - 1
     m.load_state_dict(synthetic.make_state_dict(seed=0), strict=False)
     m.H = m.W = a.size
     m.train()
@@ -70,7 +76,7 @@ def main():
         for t in z:
             t.grad = None
         mark()
-        out = m(inp, z=z)
+        out = m(inp) if a.with_encoder else m(inp, z=z)
         loss = (out["rgb"] - target).abs().mean()          # image_loss (loss_functions.py:74-80)
         mark()
         loss.backward()
@@ -121,7 +127,8 @@ def main():
     stages = {s: round(float(tms[i]), 3) for i, s in enumerate(_lib.STAGES) if cnt[i]}
     rays = a.scenes * R * world
     if rank == 0:
-        print(json.dumps({"metric": "train_step_rays_per_s (renderer fwd+bwd + optimiser step, encoder excluded)",
+        print(json.dumps({"metric": "train_step_rays_per_s (renderer fwd+bwd + optimiser step, encoder "
+                                    + ("INCLUDED: get_z fwd+bwd, 123.6 M parameters in the optimiser)" if a.with_encoder else "excluded)"),
                           "value": round(rays / ms * 1e3, 1), "unit": "rays/s", "ms_per_step": round(ms, 3), "n_gpus": world,
                           "config": {"scenes_per_gpu": a.scenes, "rays_per_scene": R, "samples": a.samples, "size": a.size,
                                      "feature_grads": not a.no_feature_grads, "precision": a.precision,
