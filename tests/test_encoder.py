@@ -181,3 +181,35 @@ def test_channels_last_maps_render_identically(precision):
         c = m(inp, z=zc)
     for k in ("rgb", "depth_ray", "at_wt", "valid_mask"):
         assert torch.equal(a[k], c[k]), k
+
+
+@pytest.mark.skipif(not os.path.isdir(gold.REF), reason="reference sources not present (GPU box)")
+@pytest.mark.parametrize("nviews,flags", [(2, {}), (3, {"no_multiview": True, "no_high_freq": True})])
+def test_get_z_matches_the_reference_get_z(nviews, flags):
+    """``CrossAttentionRenderer.get_z`` of the UNMODIFIED reference (models.py:148-188: relative poses, ImageNet
+    normalisation, encoder call, conv_map, no_multiview / no_high_freq) with the reference's own DPT wrapper as its
+    encoder, against this module's get_z (2 and 3 context views; n_view = 1 passes as well, left out for run time)."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("oracle/_ref not built")
+    torch.manual_seed(7)
+    ours_m = CrossAttentionRenderer(n_view=nviews, npoints=8, encoder="dpt_hybrid", **flags).eval()
+    sd = synthetic.make_state_dict(seed=7, n_view=nviews)
+    ref_m = ref_loader.build_model(sd, 256, 8, n_view=nviews, **flags)
+    with gold.reference_midas() as dpt_depth:
+        ref_enc = dpt_depth.DPTDepthModel(path=None, backbone="vitb_rn50_384", non_negative=True).eval()
+        ref_enc.load_state_dict(ours_m.encoder.state_dict(), strict=True)
+        ref_m.encoder = ref_enc
+        ref_m.conv_map.load_state_dict(ours_m.conv_map.state_dict())
+        inp = synthetic.make_inputs(1, 256, 4, seed=5, n_ctx=nviews)
+        inp["context"]["rgb"] = torch.rand(1, nviews, 256, 256, 3, generator=torch.Generator().manual_seed(9)) * 2 - 1
+        with torch.no_grad():
+            z_ref = ref_m.get_z(inp)
+            z = ours_m.get_z(inp)
+    assert len(z) == len(z_ref) == 3 and (ref_m.H, ref_m.W) == (ours_m.H, ours_m.W) == (256, 256)
+    for a, r in zip(z, z_ref):
+        assert a.shape == r.shape
+        scale = float(r.abs().max())
+        assert float((a - r).abs().max()) <= 2e-5 * max(scale, 1e-6)
+    if flags.get("no_high_freq"):
+        assert float(z[2].abs().max()) == 0.0
